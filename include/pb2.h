@@ -1,0 +1,192 @@
+/* pb2 — the C ABI of the B200-native path-tracing back end.
+ *
+ * This is the boundary the reference's kept C++ surface (Pupil::world::World, Pupil::pt::PTPass,
+ * Pupil::BufferManager — re-implemented in pupiloptixlab_b200/host/) calls instead of OptiX 7.5:
+ * plain pointers and sizes, `int` status codes (0 = ok, message via pb2_last_error()), no C++ or
+ * torch types.  The caller owns every host array (copied during the call); the library owns all
+ * device memory except buffers explicitly passed in as device pointers.  One host thread per scene
+ * handle.  Citations name the reference interface each entry point replaces
+ * (paths relative to the reference root).
+ *
+ * Enum values are the reference's own:
+ *   material type  Pupil::EMatType        framework/render/material/predefine.h:15-22
+ *   texture type   util::ETextureType     framework/util/texture.h:21-25
+ *   emitter type   optix::EEmitterType    framework/render/emitter/types.h:7-15
+ */
+#ifndef PB2_H
+#define PB2_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_OK 0
+#define PB2_ERR_CUDA 1
+#define PB2_ERR_ARG 2
+#define PB2_ERR_STATE 3
+
+enum { PB2_MAT_UNKNOWN = 0, PB2_MAT_DIFFUSE = 1, PB2_MAT_DIELECTRIC = 2, PB2_MAT_ROUGH_DIELECTRIC = 3, PB2_MAT_CONDUCTOR = 4,
+       PB2_MAT_ROUGH_CONDUCTOR = 5, PB2_MAT_PLASTIC = 6, PB2_MAT_ROUGH_PLASTIC = 7 };
+enum { PB2_TEX_RGB = 0, PB2_TEX_BITMAP = 1, PB2_TEX_CHECKERBOARD = 2 };
+enum { PB2_EMIT_NONE = 0, PB2_EMIT_TRI = 1, PB2_EMIT_SPHERE = 2, PB2_EMIT_CONST_ENV = 3, PB2_EMIT_ENV_MAP = 4 };
+
+/* instance flags */
+#define PB2_INST_FLIP_NORMALS 1u /* TriMesh::flip_normals / Sphere::flip_normal, framework/render/geometry.h:19,26 */
+#define PB2_INST_FLIP_TEX 2u     /* TriMesh::flip_tex_coords, geometry.h:20 */
+#define PB2_MESH_SPHERE 0xFFFFFFFFu /* mesh id of the analytic unit sphere (centre 0, radius 1), world/render_object.cpp:30-35 */
+
+/* cuda::Texture, framework/cuda/texture.h:10-31 — RGB constant or checkerboard; r0/r1 = rows 0 and 1 of
+ * the to_uv transform (the only rows Sample() reads, :34-36). */
+typedef struct pb2_texture {
+    int32_t type;
+    float a[3]; /* rgb | patch1 */
+    float b[3]; /*       patch2 */
+    float r0[4], r1[4];
+} pb2_texture;
+
+/* optix::material::Material after LoadMaterial (framework/render/material/optix_material.h:10-33,
+ * optix_material.cpp:41-130), flattened.  Texture slots by type — tex[0] is always the texture
+ * LocalBsdf::GetAlbedo() returns (optix_material.h:93-111):
+ *   diffuse          tex0 reflectance
+ *   dielectric       tex0 specular_reflectance  tex1 specular_transmittance
+ *   roughdielectric  tex0 specular_reflectance  tex1 specular_transmittance  tex2 alpha
+ *   conductor        tex0 specular_reflectance  tex1 eta  tex2 k
+ *   roughconductor   tex0 specular_reflectance  tex1 eta  tex2 k  tex3 alpha
+ *   plastic          tex0 diffuse_reflectance   tex1 specular_reflectance
+ *   roughplastic     tex0 diffuse_reflectance   tex1 specular_reflectance    tex2 alpha */
+typedef struct pb2_material {
+    int32_t type;
+    int32_t twosided;
+    float eta;                      /* int_ior / ext_ior */
+    int32_t nonlinear;
+    float int_fdr;                  /* m_int_fdr */
+    float specular_sampling_weight; /* m_specular_sampling_weight */
+    pb2_texture tex[4];
+} pb2_material;
+
+/* optix::Emitter, framework/render/emitter.h:13-23 with emitter/{area,sphere,env}.h payloads */
+typedef struct pb2_emitter {
+    int32_t type;
+    float weight, select_probability;
+    pb2_texture radiance; /* const env: radiance.a = color */
+    float area;
+    float pos[3][3], nrm[3][3], uv[3][2]; /* TriArea: world-space v0..v2 */
+    float center[3], radius;              /* Sphere */
+} pb2_emitter;
+
+typedef struct pb2_hit {
+    float t, u, v;
+    int32_t inst, prim; /* inst = -1: miss */
+} pb2_hit;
+
+/* pt::OptixLaunchParams, example/path_tracer/type.h:9-33 (the camera, emitter group and AS handle live
+ * in the scene handle).  Buffers are DEVICE pointers, row-major, pixel_index = y*width + x, row 0 = bottom. */
+typedef struct pb2_launch_params {
+    uint32_t max_depth;
+    uint32_t accumulate;   /* 0: overwrite, 1: running mean (main.cu:190-194), 2: plain sum (multi-GPU shards) */
+    uint32_t width, height;
+    uint32_t random_seed;  /* seed of the first frame */
+    uint32_t seed_stride;  /* frame i uses random_seed + i*seed_stride (0 is read as 1) */
+    uint32_t sample_cnt;   /* frames already in accum_buffer */
+    uint32_t n_frames;     /* consecutive PTPass::OnRun calls to execute (>= 1) */
+    void *accum_buffer;    /* float4, required */
+    void *frame_buffer;    /* float4, may be NULL */
+    void *normal_buffer;   /* float3, may be NULL */
+    void *albedo_buffer;   /* float3, may be NULL */
+    void *test_buffer;     /* float,  may be NULL */
+} pb2_launch_params;
+
+typedef struct pb2_build_stats {
+    uint64_t n_prims, n_triangles, n_spheres;
+    uint64_t n_nodes;      /* BVH8 nodes (80 B each) */
+    uint64_t bvh_bytes;    /* nodes + primitive records */
+    float build_ms;        /* device time, CUDA events around the whole build */
+    float sah_cost;        /* SAH cost of the wide tree (node cost 1, primitive cost 1), root area normalised */
+    uint32_t max_depth;    /* depth of the wide tree */
+} pb2_build_stats;
+
+typedef struct pb2_render_stats {
+    uint64_t closest_rays, shadow_rays; /* rays traced by the last pb2_render call */
+    uint64_t kernel_launches;           /* kernels launched by the last pb2_render call */
+    float total_ms;                     /* device time of the last pb2_render call (CUDA events on the scene's stream) */
+    float generate_ms, extend_ms, shade_ms, shadow_ms, accumulate_ms; /* per stage, only when profiling is on */
+    uint64_t nodes_visited, prims_tested;                             /* traversal counters, only when counting is on */
+} pb2_render_stats;
+
+/* ---- library / device ------------------------------------------------------------------------------- */
+/* replaces cuda::Context::Init + optix::Context::Init (framework/cuda/context.cpp:15-44, optix/context.cpp:38-50) */
+int pb2_init(int device);
+const char *pb2_last_error(void);
+int pb2_device_count(void);
+
+/* ---- device memory (BufferManager / CudaMemcpyToDevice, framework/system/buffer.cpp:39-99, cuda/util.h:40-75) */
+int pb2_malloc(void **dptr, uint64_t bytes); /* zero-initialised, like Buffer allocation (buffer.cpp:44-45) */
+int pb2_free(void *dptr);
+int pb2_upload(void *dptr, const void *host, uint64_t bytes);
+int pb2_download(void *host, const void *dptr, uint64_t bytes);
+int pb2_memset(void *dptr, int value, uint64_t bytes);
+
+/* ---- scene ------------------------------------------------------------------------------------------ */
+typedef struct pb2_scene pb2_scene;
+int pb2_scene_create(pb2_scene **scene);
+int pb2_scene_destroy(pb2_scene *scene);
+int pb2_scene_clear(pb2_scene *scene);
+/* run the scene's kernels on an existing CUDA stream (cudaStream_t); NULL restores the scene's own stream.
+ * replaces cuda::Stream (framework/cuda/stream.cpp:8) */
+int pb2_scene_set_stream(pb2_scene *scene, void *cuda_stream);
+
+/* object-space triangle mesh shared by instances: ShapeManager mesh data + CudaShapeDataManager upload
+ * (framework/resource/shape.cpp:193-226,268-327).  nrm / uv may be NULL. */
+int pb2_scene_add_mesh(pb2_scene *scene, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t n_vertices,
+                       uint32_t n_triangles, uint32_t *mesh_id);
+/* one RenderObject (framework/world/render_object.cpp:18-65) + its SBT hit record
+ * (example/path_tracer/pt_pass.cpp:180-207): geometry, 3x4 object->world transform (row-major),
+ * material, emitter_index_offset (-1: not an emitter).  mesh_id = PB2_MESH_SPHERE for spheres. */
+int pb2_scene_add_instance(pb2_scene *scene, uint32_t mesh_id, const float xform[12], uint32_t flags, const pb2_material *material,
+                           int32_t emitter_index_offset, uint32_t *instance_id);
+/* EmitterHelper::GetEmitterGroup (framework/world/emitter.cpp:339-390); env may be NULL */
+int pb2_scene_set_emitters(pb2_scene *scene, const pb2_emitter *areas, uint32_t n_areas, const pb2_emitter *env);
+/* CameraHelper::GetCudaMemory (framework/world/camera.cpp:72-93): two row-major 4x4 */
+int pb2_scene_set_camera(pb2_scene *scene, const float sample_to_camera[16], const float camera_to_world[16]);
+
+/* replaces GAS::Create + IAS::Create (framework/world/gas_manager.cpp:69-245, ias_manager.cpp:29-114):
+ * GPU build of one world-space compressed 8-wide BVH over every instance.  stats may be NULL. */
+int pb2_bvh_build(pb2_scene *scene, pb2_build_stats *stats);
+/* builder: 0 = LBVH (Morton order), 1 = binned SAH (default) */
+int pb2_scene_set_builder(pb2_scene *scene, int builder);
+
+/* parity / benchmark hooks for the two optixTrace flavours (main.cu:80-85,161-166; emitter.h:91-100).
+ * rays: n x 8 floats (ox oy oz tmin dx dy dz tmax).  Host-pointer versions copy in and out. */
+int pb2_trace_closest(pb2_scene *scene, const float *rays, uint64_t n, pb2_hit *hits);
+int pb2_trace_any(pb2_scene *scene, const float *rays, uint64_t n, uint8_t *occluded);
+/* device-pointer versions: rays_dev float4[2n]; hits_tuvp float4[n] (t,u,v,bits(prim)); hits_inst int32[n];
+ * asynchronous on the scene's stream */
+int pb2_trace_closest_dev(pb2_scene *scene, const void *rays_dev, uint64_t n, void *hits_tuvp_dev, void *hits_inst_dev);
+int pb2_trace_any_dev(pb2_scene *scene, const void *rays_dev, uint64_t n, void *occluded_u32_dev);
+/* read back the wide BVH (for the oracle-side node/primitive counters): sizes first with NULL pointers */
+int pb2_bvh_download(pb2_scene *scene, void *nodes, uint64_t *n_nodes, void *prims, uint64_t *n_prims);
+
+/* ---- rendering -------------------------------------------------------------------------------------- */
+/* replaces optix::Pass::Run + Synchronize (framework/optix/pass.h:71-93) as driven by PTPass::OnRun
+ * (example/path_tracer/pt_pass.cpp:39-57): executes params->n_frames frames.  pb2_render is asynchronous on
+ * the scene's stream; pb2_synchronize waits. */
+int pb2_render(pb2_scene *scene, const pb2_launch_params *params);
+int pb2_synchronize(pb2_scene *scene);
+int pb2_render_stats_get(pb2_scene *scene, pb2_render_stats *stats); /* synchronises */
+/* options: profiling (per-stage events, serialises stages), counting (traversal counters),
+ * paths_in_flight (0 = default), sort_by_material (default 1) */
+int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value);
+/* multi-GPU shards render with accumulate = 2 (sum); after the cross-GPU reduction the root calls this:
+ * frame[i] = (sum[i].xyz / total_spp, 1).   */
+int pb2_finalize_sum(pb2_scene *scene, const void *sum_buffer, void *frame_buffer, uint64_t n_pixels, uint32_t total_spp);
+
+/* per-function device known-answer hooks (tests only): run the device restatement of one function of
+ * framework/render/material, framework/render/emitter, framework/optix/util.h, framework/cuda/random.h over
+ * n inputs.  `what` selects the function; layouts are documented next to pb2_kat in csrc/kat.cu. */
+int pb2_kat(const char *what, const void *in0, const void *in1, const void *in2, uint64_t n, void *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -120,6 +120,7 @@ int orc_get_env_emitter(void *sp, orc_emitter *out) {
     if (s->has_env) *out = s->env;
     return s->has_env;
 }
+void orc_get_instance_xform(void *s, int i, float *out16) { std::memcpy(out16, static_cast<SceneT *>(s)->instances[i].xf.e, 64); }
 int orc_num_instances(void *s) { return (int)static_cast<SceneT *>(s)->instances.size(); }
 uint64_t orc_num_triangles(void *s) { return static_cast<SceneT *>(s)->tris.size(); }
 

@@ -1,0 +1,90 @@
+"""In-tree builds (no JIT cache): the CUDA back end libpb2.so for sm_100a and the C++ host library.
+
+    python -m pupiloptixlab_b200.build [--force]
+
+Outputs go to pupiloptixlab_b200/_build/ (git-ignored; they travel to the GPU box with the snapshot).
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+BUILD = PKG / "_build"
+CSRC = PKG / "csrc"
+HOST = PKG / "host"
+
+NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
+CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
+
+
+def _newer(target: Path, deps) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(d).stat().st_mtime > t for d in deps)
+
+
+def _run(cmd, log: Path | None = None):
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if log is not None:
+        log.write_text(" ".join(map(str, cmd)) + "\n" + r.stdout + r.stderr)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError(f"build step failed: {' '.join(map(str, cmd))}")
+    return r
+
+
+def build_pb2(force: bool = False) -> Path:
+    BUILD.mkdir(exist_ok=True)
+    out = BUILD / "libpb2.so"
+    srcs = sorted(CSRC.glob("*.cu"))
+    hdrs = sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "pb2.h"]
+    objs = []
+
+    def compile_one(src: Path):
+        obj = BUILD / (src.stem + ".o")
+        if force or _newer(obj, [src, *hdrs]):
+            _run([NVCC, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)], BUILD / (src.stem + ".ptxas.log"))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    if force or _newer(out, objs):
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *map(str, objs), "-o", str(out), "-lcudart"])
+    return out
+
+
+def build_host(force: bool = False) -> Path | None:
+    srcs = sorted(HOST.glob("*.cpp"))
+    if not srcs:
+        return None
+    BUILD.mkdir(exist_ok=True)
+    out = BUILD / "libpupil_host.so"
+    hdrs = sorted(HOST.glob("*.h")) + sorted((ROOT / "include").glob("*.h"))
+    if force or _newer(out, [*srcs, *hdrs]):
+        _run([CXX, "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unused-function", f"-I{ROOT / 'include'}", f"-I{HOST}",
+              *map(str, srcs), "-o", str(out), f"-L{BUILD}", "-lpb2", f"-Wl,-rpath,$ORIGIN"])
+    return out
+
+
+def build_oracle() -> None:
+    subprocess.run(["make", "-C", str(ROOT / "oracle"), "all"], check=True, capture_output=True)
+
+
+def build_all(force: bool = False) -> None:
+    build_pb2(force)
+    build_host(force)
+    build_oracle()
+
+
+if __name__ == "__main__":
+    build_all("--force" in sys.argv)
+    print("built:", *sorted(p.name for p in BUILD.glob("*.so")))

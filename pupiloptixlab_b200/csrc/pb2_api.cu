@@ -1,0 +1,385 @@
+// extern "C" surface of libpb2.so (include/pb2.h): argument checking, exception -> status code mapping,
+// host <-> device conversion of the POD records.  No compute lives here.
+#include "scene.cuh"
+#include <cstring>
+#include <mutex>
+
+namespace pb2 {
+void collect_render_stats(Scene &s); // wavefront.cu
+
+DevTexture to_dev(const pb2_texture &t) {
+    DevTexture d;
+    float type_bits;
+    memcpy(&type_bits, &t.type, 4);
+    d.hdr = make_float4(type_bits, t.a[0], t.a[1], t.a[2]);
+    d.b = make_float4(t.b[0], t.b[1], t.b[2], 0.f);
+    d.r0 = make_float4(t.r0[0], t.r0[1], t.r0[2], t.r0[3]);
+    d.r1 = make_float4(t.r1[0], t.r1[1], t.r1[2], t.r1[3]);
+    return d;
+}
+static DevMaterial to_dev(const pb2_material &m) {
+    DevMaterial d{};
+    d.type = m.type, d.twosided = m.twosided, d.eta = m.eta, d.nonlinear = m.nonlinear;
+    d.int_fdr = m.int_fdr, d.specular_sampling_weight = m.specular_sampling_weight;
+    for (int i = 0; i < 4; ++i) d.tex[i] = to_dev(m.tex[i]);
+    return d;
+}
+DevEmitter to_dev(const pb2_emitter &e) {
+    DevEmitter d{};
+    d.type = e.type, d.weight = e.weight, d.select_probability = e.select_probability, d.area = e.area;
+    d.radiance = to_dev(e.radiance);
+    d.p0 = make_float4(e.pos[0][0], e.pos[0][1], e.pos[0][2], e.uv[0][0]);
+    d.p1 = make_float4(e.pos[1][0], e.pos[1][1], e.pos[1][2], e.uv[0][1]);
+    d.p2 = make_float4(e.pos[2][0], e.pos[2][1], e.pos[2][2], e.uv[1][0]);
+    d.n0 = make_float4(e.nrm[0][0], e.nrm[0][1], e.nrm[0][2], e.uv[1][1]);
+    d.n1 = make_float4(e.nrm[1][0], e.nrm[1][1], e.nrm[1][2], e.uv[2][0]);
+    d.n2 = make_float4(e.nrm[2][0], e.nrm[2][1], e.nrm[2][2], e.uv[2][1]);
+    d.center_r = make_float4(e.center[0], e.center[1], e.center[2], e.radius);
+    return d;
+}
+
+Scene::Scene() {
+    PB2_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    stream = own_stream;
+}
+Scene::~Scene() {
+    if (wf) wavefront_destroy(wf);
+    if (own_stream) cudaStreamDestroy(own_stream);
+}
+void Scene::upload_tables() {
+    if (!tables_dirty) return;
+    d_inst.upload(h_inst.data(), h_inst.size(), stream);
+    d_mat.upload(h_mat.data(), h_mat.size(), stream);
+    d_areas.upload(h_areas.data(), h_areas.size(), stream);
+    if (has_env) d_env.upload(&h_env, 1, stream);
+    PB2_CUDA(cudaStreamSynchronize(stream)); // host vectors may change right after
+    tables_dirty = false;
+}
+SceneView Scene::view() const {
+    SceneView v{};
+    v.nodes = d_nodes.ptr, v.prims = d_prims.ptr, v.instances = d_inst.ptr, v.materials = d_mat.ptr;
+    v.areas = d_areas.ptr, v.env = has_env ? d_env.ptr : nullptr;
+    v.n_areas = (uint32_t)h_areas.size(), v.n_nodes = n_nodes, v.n_prims = n_prims;
+    return v;
+}
+}// namespace pb2
+
+using namespace pb2;
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+#define PB2_TRY try {
+#define PB2_CATCH                                                  \
+    }                                                              \
+    catch (const CudaError &e) { return fail(PB2_ERR_CUDA, e.what()); } \
+    catch (const std::exception &e) { return fail(PB2_ERR_STATE, e.what()); }
+
+static Scene *S(pb2_scene *s) { return reinterpret_cast<Scene *>(s); }
+
+// 3x4 affine inverse in fp64, rounded once (the reference lets OptiX / DirectXMath invert instance transforms)
+static bool invert_affine(const float m[12], float out[12]) {
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (det == 0.0) return false;
+    const double id = 1.0 / det;
+    const double r[9] = { (e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id, (f * g - d * i) * id, (a * i - c * g) * id,
+                          (c * d - a * f) * id, (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id };
+    const double tx = m[3], ty = m[7], tz = m[11];
+    for (int k = 0; k < 3; ++k) {
+        out[k * 4 + 0] = (float)r[k * 3], out[k * 4 + 1] = (float)r[k * 3 + 1], out[k * 4 + 2] = (float)r[k * 3 + 2];
+        out[k * 4 + 3] = (float)-(r[k * 3] * tx + r[k * 3 + 1] * ty + r[k * 3 + 2] * tz);
+    }
+    return true;
+}
+
+extern "C" {
+const char *pb2_last_error(void) { return g_last_error.c_str(); }
+
+int pb2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int pb2_init(int device) {
+    PB2_TRY
+    int n = 0;
+    PB2_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(PB2_ERR_ARG, "pb2_init: no such CUDA device");
+    PB2_CUDA(cudaSetDevice(device));
+    PB2_CUDA(cudaFree(nullptr));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_malloc(void **dptr, uint64_t bytes) {
+    PB2_TRY
+    if (!dptr) return fail(PB2_ERR_ARG, "pb2_malloc: null");
+    *dptr = nullptr;
+    if (!bytes) return PB2_OK;
+    PB2_CUDA(cudaMalloc(dptr, bytes));
+    PB2_CUDA(cudaMemset(*dptr, 0, bytes));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_free(void *dptr) {
+    PB2_TRY
+    if (dptr) PB2_CUDA(cudaFree(dptr));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_upload(void *dptr, const void *host, uint64_t bytes) {
+    PB2_TRY
+    if (bytes) PB2_CUDA(cudaMemcpy(dptr, host, bytes, cudaMemcpyHostToDevice));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_download(void *host, const void *dptr, uint64_t bytes) {
+    PB2_TRY
+    if (bytes) PB2_CUDA(cudaMemcpy(host, dptr, bytes, cudaMemcpyDeviceToHost));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_memset(void *dptr, int value, uint64_t bytes) {
+    PB2_TRY
+    if (bytes) PB2_CUDA(cudaMemset(dptr, value, bytes));
+    return PB2_OK;
+    PB2_CATCH
+}
+
+int pb2_scene_create(pb2_scene **scene) {
+    PB2_TRY
+    if (!scene) return fail(PB2_ERR_ARG, "pb2_scene_create: null");
+    *scene = reinterpret_cast<pb2_scene *>(new Scene());
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_destroy(pb2_scene *scene) {
+    PB2_TRY
+    if (scene) {
+        cudaStreamSynchronize(S(scene)->stream);
+        delete S(scene);
+    }
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_clear(pb2_scene *scene) {
+    PB2_TRY
+    Scene &s = *S(scene);
+    PB2_CUDA(cudaStreamSynchronize(s.stream));
+    s.meshes.clear(), s.h_inst.clear(), s.h_mat.clear(), s.h_areas.clear();
+    s.has_env = false, s.tables_dirty = true, s.bvh_valid = false, s.n_nodes = s.n_prims = 0;
+    s.d_nodes.release(), s.d_prims.release();
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_set_stream(pb2_scene *scene, void *cuda_stream) {
+    PB2_TRY
+    Scene &s = *S(scene);
+    PB2_CUDA(cudaStreamSynchronize(s.stream));
+    s.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s.own_stream;
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_add_mesh(pb2_scene *scene, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t n_vertices,
+                       uint32_t n_triangles, uint32_t *mesh_id) {
+    PB2_TRY
+    if (!scene || !pos || !idx || !n_vertices || !n_triangles) return fail(PB2_ERR_ARG, "pb2_scene_add_mesh: empty mesh");
+    Scene &s = *S(scene);
+    auto m = std::make_unique<Mesh>();
+    m->n_verts = n_vertices, m->n_tris = n_triangles;
+    m->pos.upload(pos, (size_t)n_vertices * 3, s.stream);
+    if (nrm) m->nrm.upload(nrm, (size_t)n_vertices * 3, s.stream);
+    if (uv) m->uv.upload(uv, (size_t)n_vertices * 2, s.stream);
+    m->idx.upload(idx, (size_t)n_triangles * 3, s.stream);
+    PB2_CUDA(cudaStreamSynchronize(s.stream)); // caller may free its arrays now
+    if (mesh_id) *mesh_id = (uint32_t)s.meshes.size();
+    s.meshes.push_back(std::move(m));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_add_instance(pb2_scene *scene, uint32_t mesh_id, const float xform[12], uint32_t flags, const pb2_material *material,
+                           int32_t emitter_index_offset, uint32_t *instance_id) {
+    PB2_TRY
+    if (!scene || !xform) return fail(PB2_ERR_ARG, "pb2_scene_add_instance: null");
+    Scene &s = *S(scene);
+    DevInstance in{};
+    float inv[12];
+    if (!invert_affine(xform, inv)) return fail(PB2_ERR_ARG, "pb2_scene_add_instance: singular transform");
+    for (int r = 0; r < 3; ++r) {
+        in.xf[r] = make_float4(xform[r * 4], xform[r * 4 + 1], xform[r * 4 + 2], xform[r * 4 + 3]);
+        in.inv[r] = make_float4(inv[r * 4], inv[r * 4 + 1], inv[r * 4 + 2], inv[r * 4 + 3]);
+    }
+    in.flags = flags & (PB2_INST_FLIP_NORMALS | PB2_INST_FLIP_TEX);
+    if (mesh_id == PB2_MESH_SPHERE) {
+        in.flags |= PB2_IF_SPHERE;
+        in.n_tris = 1;
+    } else {
+        if (mesh_id >= s.meshes.size()) return fail(PB2_ERR_ARG, "pb2_scene_add_instance: unknown mesh id");
+        const Mesh &m = *s.meshes[mesh_id];
+        in.pos = m.pos.ptr, in.nrm = m.nrm.ptr, in.uv = m.uv.ptr, in.idx = m.idx.ptr;
+        if (m.nrm.ptr) in.flags |= PB2_IF_HAS_NRM;
+        if (m.uv.ptr) in.flags |= PB2_IF_HAS_UV;
+        in.n_tris = m.n_tris;
+    }
+    pb2_material none{};
+    const pb2_material &mat = material ? *material : none;
+    if (mat.twosided) in.flags |= PB2_IF_TWOSIDED;
+    in.mat_type = mat.type;
+    in.emitter_offset = emitter_index_offset;
+    if (instance_id) *instance_id = (uint32_t)s.h_inst.size();
+    s.h_inst.push_back(in);
+    s.h_mat.push_back(to_dev(mat));
+    s.tables_dirty = true, s.bvh_valid = false;
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_set_emitters(pb2_scene *scene, const pb2_emitter *areas, uint32_t n_areas, const pb2_emitter *env) {
+    PB2_TRY
+    if (!scene || (n_areas && !areas)) return fail(PB2_ERR_ARG, "pb2_scene_set_emitters: null");
+    Scene &s = *S(scene);
+    s.h_areas.resize(n_areas);
+    for (uint32_t i = 0; i < n_areas; ++i) s.h_areas[i] = to_dev(areas[i]);
+    s.has_env = env != nullptr;
+    if (env) s.h_env = to_dev(*env);
+    s.tables_dirty = true;
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_set_camera(pb2_scene *scene, const float s2c[16], const float c2w[16]) {
+    PB2_TRY
+    if (!scene || !s2c || !c2w) return fail(PB2_ERR_ARG, "pb2_scene_set_camera: null");
+    Scene &s = *S(scene);
+    for (int r = 0; r < 4; ++r) {
+        s.cam.s2c[r] = make_float4(s2c[r * 4], s2c[r * 4 + 1], s2c[r * 4 + 2], s2c[r * 4 + 3]);
+        s.cam.c2w[r] = make_float4(c2w[r * 4], c2w[r * 4 + 1], c2w[r * 4 + 2], c2w[r * 4 + 3]);
+    }
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_set_builder(pb2_scene *scene, int builder) {
+    if (!scene || builder < 0 || builder > 1) return fail(PB2_ERR_ARG, "pb2_scene_set_builder: 0 = LBVH, 1 = binned SAH");
+    S(scene)->builder = builder;
+    S(scene)->bvh_valid = false;
+    return PB2_OK;
+}
+int pb2_bvh_build(pb2_scene *scene, pb2_build_stats *stats) {
+    PB2_TRY
+    if (!scene) return fail(PB2_ERR_ARG, "pb2_bvh_build: null");
+    build_bvh(*S(scene));
+    if (stats) *stats = S(scene)->build_stats;
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_trace_closest_dev(pb2_scene *scene, const void *rays_dev, uint64_t n, void *hits_tuvp_dev, void *hits_inst_dev) {
+    PB2_TRY
+    trace_closest_dev(*S(scene), static_cast<const float4 *>(rays_dev), n, static_cast<float4 *>(hits_tuvp_dev), static_cast<int32_t *>(hits_inst_dev));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_trace_any_dev(pb2_scene *scene, const void *rays_dev, uint64_t n, void *occluded_u32_dev) {
+    PB2_TRY
+    trace_any_dev(*S(scene), static_cast<const float4 *>(rays_dev), n, static_cast<uint32_t *>(occluded_u32_dev));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_trace_closest(pb2_scene *scene, const float *rays, uint64_t n, pb2_hit *hits) {
+    PB2_TRY
+    if (!scene || (n && (!rays || !hits))) return fail(PB2_ERR_ARG, "pb2_trace_closest: null");
+    Scene &s = *S(scene);
+    if (!n) return PB2_OK;
+    DevBuf<float4> d_rays(n * 2), d_tuvp(n);
+    DevBuf<int32_t> d_inst(n);
+    PB2_CUDA(cudaMemcpyAsync(d_rays.ptr, rays, n * 32, cudaMemcpyHostToDevice, s.stream));
+    trace_closest_dev(s, d_rays.ptr, n, d_tuvp.ptr, d_inst.ptr);
+    std::vector<float4> tuvp(n);
+    std::vector<int32_t> inst(n);
+    PB2_CUDA(cudaMemcpyAsync(tuvp.data(), d_tuvp.ptr, n * 16, cudaMemcpyDeviceToHost, s.stream));
+    PB2_CUDA(cudaMemcpyAsync(inst.data(), d_inst.ptr, n * 4, cudaMemcpyDeviceToHost, s.stream));
+    PB2_CUDA(cudaStreamSynchronize(s.stream));
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t prim;
+        memcpy(&prim, &tuvp[i].w, 4);
+        hits[i] = pb2_hit{ tuvp[i].x, tuvp[i].y, tuvp[i].z, inst[i], inst[i] < 0 ? -1 : (int32_t)prim };
+    }
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_trace_any(pb2_scene *scene, const float *rays, uint64_t n, uint8_t *occluded) {
+    PB2_TRY
+    if (!scene || (n && (!rays || !occluded))) return fail(PB2_ERR_ARG, "pb2_trace_any: null");
+    Scene &s = *S(scene);
+    if (!n) return PB2_OK;
+    DevBuf<float4> d_rays(n * 2);
+    DevBuf<uint32_t> d_occ(n);
+    PB2_CUDA(cudaMemcpyAsync(d_rays.ptr, rays, n * 32, cudaMemcpyHostToDevice, s.stream));
+    trace_any_dev(s, d_rays.ptr, n, d_occ.ptr);
+    std::vector<uint32_t> occ(n);
+    PB2_CUDA(cudaMemcpyAsync(occ.data(), d_occ.ptr, n * 4, cudaMemcpyDeviceToHost, s.stream));
+    PB2_CUDA(cudaStreamSynchronize(s.stream));
+    for (uint64_t i = 0; i < n; ++i) occluded[i] = (uint8_t)occ[i];
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_bvh_download(pb2_scene *scene, void *nodes, uint64_t *n_nodes, void *prims, uint64_t *n_prims) {
+    PB2_TRY
+    Scene &s = *S(scene);
+    if (!s.bvh_valid) return fail(PB2_ERR_STATE, "pb2_bvh_download: no BVH");
+    if (n_nodes) *n_nodes = s.n_nodes;
+    if (n_prims) *n_prims = s.n_prims;
+    PB2_CUDA(cudaStreamSynchronize(s.stream));
+    if (nodes && s.n_nodes) PB2_CUDA(cudaMemcpy(nodes, s.d_nodes.ptr, (size_t)s.n_nodes * sizeof(Bvh8Node), cudaMemcpyDeviceToHost));
+    if (prims && s.n_prims) PB2_CUDA(cudaMemcpy(prims, s.d_prims.ptr, (size_t)s.n_prims * sizeof(PrimRec), cudaMemcpyDeviceToHost));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_render(pb2_scene *scene, const pb2_launch_params *params) {
+    PB2_TRY
+    if (!scene || !params) return fail(PB2_ERR_ARG, "pb2_render: null");
+    render(*S(scene), *params);
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_synchronize(pb2_scene *scene) {
+    PB2_TRY
+    PB2_CUDA(cudaStreamSynchronize(S(scene)->stream));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_render_stats_get(pb2_scene *scene, pb2_render_stats *stats) {
+    PB2_TRY
+    if (!scene || !stats) return fail(PB2_ERR_ARG, "pb2_render_stats_get: null");
+    collect_render_stats(*S(scene));
+    *stats = S(scene)->render_stats;
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
+    if (!scene || !name) return fail(PB2_ERR_ARG, "pb2_scene_set_option: null");
+    Scene &s = *S(scene);
+    const std::string n = name;
+    if (n == "profiling") s.profiling = value != 0;
+    else if (n == "counting") s.counting = value != 0;
+    else if (n == "sort_by_material") s.sort_by_material = value != 0;
+    else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);
+    else return fail(PB2_ERR_ARG, "pb2_scene_set_option: unknown option " + n);
+    return PB2_OK;
+}
+int pb2_finalize_sum(pb2_scene *scene, const void *sum_buffer, void *frame_buffer, uint64_t n_pixels, uint32_t total_spp) {
+    PB2_TRY
+    if (!scene || !sum_buffer || !frame_buffer || !total_spp) return fail(PB2_ERR_ARG, "pb2_finalize_sum: bad argument");
+    finalize_sum(*S(scene), static_cast<const float4 *>(sum_buffer), static_cast<float4 *>(frame_buffer), n_pixels, total_spp);
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_kat(const char *what, const void *in0, const void *in1, const void *in2, uint64_t n, void *out) {
+    PB2_TRY
+    if (!what || !out) return fail(PB2_ERR_ARG, "pb2_kat: null");
+    return run_kat(what, in0, in1, in2, n, out);
+    PB2_CATCH
+}
+}

@@ -1,0 +1,66 @@
+// Host-side scene object behind the pb2 C ABI.
+#pragma once
+#include "pb2_types.cuh"
+#include "util.cuh"
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace pb2 {
+
+struct Mesh {
+    DevBuf<float> pos, nrm, uv;
+    DevBuf<uint32_t> idx;
+    uint32_t n_verts = 0, n_tris = 0;
+};
+
+struct Wavefront; // wavefront.cu
+
+struct Scene {
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::vector<std::unique_ptr<Mesh>> meshes;
+    std::vector<DevInstance> h_inst;
+    std::vector<DevMaterial> h_mat;
+    std::vector<DevEmitter> h_areas;
+    bool has_env = false;
+    DevEmitter h_env{};
+    Camera cam{};
+
+    DevBuf<DevInstance> d_inst;
+    DevBuf<DevMaterial> d_mat;
+    DevBuf<DevEmitter> d_areas, d_env;
+    bool tables_dirty = true;
+
+    DevBuf<Bvh8Node> d_nodes;
+    DevBuf<PrimRec> d_prims;
+    uint32_t n_nodes = 0, n_prims = 0;
+    bool bvh_valid = false;
+    int builder = 1; // 0 LBVH, 1 binned SAH
+    pb2_build_stats build_stats{};
+
+    // options
+    bool profiling = false, counting = false, sort_by_material = true;
+    uint64_t paths_in_flight = 0;
+    int trace_block = 0; // 0 = default
+
+    Wavefront *wf = nullptr;
+    pb2_render_stats render_stats{};
+
+    Scene();
+    ~Scene();
+    void upload_tables();
+    SceneView view() const;
+};
+
+// bvh_build.cu
+void build_bvh(Scene &s);
+// trace.cu
+void trace_closest_dev(Scene &s, const float4 *rays, uint64_t n, float4 *hit_tuvp, int32_t *hit_inst);
+void trace_any_dev(Scene &s, const float4 *rays, uint64_t n, uint32_t *occluded);
+// wavefront.cu
+void render(Scene &s, const pb2_launch_params &p);
+void finalize_sum(Scene &s, const float4 *sum, float4 *frame, uint64_t n, uint32_t spp);
+void wavefront_destroy(Wavefront *wf);
+// kat.cu
+int run_kat(const char *what, const void *in0, const void *in1, const void *in2, uint64_t n, void *out);
+}// namespace pb2

@@ -1,0 +1,584 @@
+// Wavefront pt-with-MIS integrator: the replacement for the reference's OptiX megakernel
+// (__raygen__main / __miss__default / __closesthit__default, example/path_tracer/main.cu:38-234), one
+// optixLaunch + cudaStreamSynchronize per sample (example/path_tracer/pt_pass.cpp:51-53).
+//
+// A render call executes `n_frames` frames (= samples per pixel, one RNG seed each) in batches of S
+// frames; a batch is S*W*H paths living in SoA arrays indexed by path slot p = frame*W*H + pixel.
+// Per bounce three kernels run over index queues (no host round trip: queue sizes stay on the device,
+// grids are sized for the worst case and exit early):
+//   extend   closest-hit traversal of the extension rays; appends each path to the queue of the hit
+//            material type (0 = miss) with warp-aggregated atomics  -> material-sorted shading
+//   shade    hit geometry + BSDF; emission with MIS; Russian roulette; light sampling (emits a shadow ray
+//            with its pending contribution); BSDF sampling (emits the next extension ray)
+//   shadow   any-hit traversal; unoccluded rays add their contribution to the path radiance
+// and one `accumulate` kernel per batch folds the per-path radiance into the accumulation buffer in
+// frame order with the reference's running-mean formula (main.cu:190-196).
+//
+// RNG draw order, depth semantics, asymmetric MIS and every other observable quirk follow main.cu
+// line by line; see the comments in k_shade.
+#include "scene.cuh"
+#include "pt_math.cuh"
+#include "traverse.cuh"
+#include <algorithm>
+
+namespace pb2 {
+
+constexpr int kNumTypes = 8; // queue 0 = miss, 1..7 = EMatType
+constexpr int kCtrPerRound = 16;
+// per-round counter slots
+enum { CTR_EXT = 0, CTR_SHADOW = 1, CTR_MAT0 = 2 /* ..9 */ };
+
+struct Wavefront {
+    uint64_t capacity = 0;
+    DevBuf<float4> ray_o, ray_d, hit_tuvp, thr, rad, sh_o, sh_d, sh_c;
+    DevBuf<int32_t> hit_inst;
+    DevBuf<uint32_t> rng, state;
+    DevBuf<uint32_t> q_ext[2], q_shadow, q_mat;
+    DevBuf<uint32_t> counters; // (max_depth + 2) rounds x kCtrPerRound
+    DevBuf<unsigned long long> trav_counters, ray_totals;
+    uint32_t rounds_alloc = 0;
+    struct Ev {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<Ev> events;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    uint64_t launches = 0;
+    uint32_t rounds_used = 0, batches = 0;
+    bool stats_pending = false;
+
+    void ensure(uint64_t paths, uint32_t rounds) {
+        if (paths > capacity) {
+            capacity = paths;
+            ray_o.alloc(paths), ray_d.alloc(paths), hit_tuvp.alloc(paths), thr.alloc(paths), rad.alloc(paths);
+            sh_o.alloc(paths), sh_d.alloc(paths), sh_c.alloc(paths), hit_inst.alloc(paths), rng.alloc(paths), state.alloc(paths);
+            q_ext[0].alloc(paths), q_ext[1].alloc(paths), q_shadow.alloc(paths), q_mat.alloc(paths * kNumTypes);
+        }
+        if (rounds > rounds_alloc) {
+            rounds_alloc = rounds;
+            counters.alloc((size_t)rounds * kCtrPerRound);
+        }
+        if (!trav_counters.ptr) trav_counters.alloc(4), ray_totals.alloc(2);
+        if (!t0) {
+            PB2_CUDA(cudaEventCreate(&t0));
+            PB2_CUDA(cudaEventCreate(&t1));
+        }
+    }
+    ~Wavefront() {
+        for (auto &e : events) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+        if (t0) cudaEventDestroy(t0), cudaEventDestroy(t1);
+    }
+};
+void wavefront_destroy(Wavefront *wf) { delete wf; }
+
+namespace {
+
+struct PathArrays {
+    float4 *ray_o, *ray_d, *hit_tuvp, *thr, *rad, *sh_o, *sh_d, *sh_c;
+    int32_t *hit_inst;
+    uint32_t *rng, *state;
+};
+struct FrameParams {
+    uint32_t width, height, n_pixels;
+    uint32_t max_depth;
+    uint32_t first_seed, seed_stride;
+    uint32_t frames; // frames in this batch
+};
+
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+// warp-aggregated appends, called by all 32 lanes of a converged warp: one atomicAdd per warp (per
+// distinct key for the keyed version); lanes with pred == false get no slot.
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, bool pred) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    if (!mask) return 0;
+    const int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if ((int)(threadIdx.x & 31) == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & lanemask_lt());
+}
+__device__ __forceinline__ uint32_t warp_append_keyed(uint32_t *counters, uint32_t key, bool pred) {
+    const uint32_t peers = __match_any_sync(0xffffffffu, pred ? key : 0xffffffffu);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (pred && (int)(threadIdx.x & 31) == leader) base = atomicAdd(&counters[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & lanemask_lt());
+}
+
+// ---- generate: main.cu:50-78 ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_generate(PathArrays pa, FrameParams fp, Camera cam, uint32_t *__restrict__ q_ext, uint32_t n_paths) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x) {
+        const uint32_t frame = p / fp.n_pixels, pixel = p - frame * fp.n_pixels;
+        const uint32_t y = pixel / fp.width, x = pixel - y * fp.width;
+        uint32_t rng = rng_init(4, pixel, fp.first_seed + frame * fp.seed_stride); // :55
+        const float jx = rng_next(rng), jy = rng_next(rng);                         // :58 (x drawn first)
+        const float4 pf = make_float4((static_cast<float>(x) + jx) / static_cast<float>(fp.width),
+                                      (static_cast<float>(y) + jy) / static_cast<float>(fp.height), 0.f, 1.f);
+        float4 d = make_float4(dot(cam.s2c[0], pf), dot(cam.s2c[1], pf), dot(cam.s2c[2], pf), dot(cam.s2c[3], pf)); // :67
+        const float inv = 1.0f / d.w;                                                                               // :69
+        d = make_float4(d.x * inv, d.y * inv, d.z * inv, 0.f);                                                      // :70
+        const float inv_len = 1.0f / sqrtf(dot(d, d));                                                              // :71
+        d = make_float4(d.x * inv_len, d.y * inv_len, d.z * inv_len, 0.f);
+        const float3 dir = normalize(mk3(dot(cam.c2w[0], d), dot(cam.c2w[1], d), dot(cam.c2w[2], d))); // :73
+        pa.ray_o[p] = make_float4(cam.c2w[0].w, cam.c2w[1].w, cam.c2w[2].w, 0.001f);                    // :75-78, tmin :82
+        pa.ray_d[p] = make_float4(dir.x, dir.y, dir.z, 1e16f);
+        pa.thr[p] = make_float4(1.f, 1.f, 1.f, 0.f);
+        pa.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pa.rng[p] = rng;
+        pa.state[p] = 0u;
+        q_ext[p] = p;
+    }
+}
+
+// ---- extend ------------------------------------------------------------------------------------------------
+template<bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(SceneView sv, PathArrays pa, const uint32_t *__restrict__ q_in, const uint32_t *__restrict__ n_in,
+                                                uint32_t *__restrict__ q_mat, uint32_t *__restrict__ mat_counts, uint32_t capacity, int sort,
+                                                unsigned long long *__restrict__ trav) {
+    const uint32_t n = *n_in;
+    TraceCounters ctr{ 0, 0 };
+    // warp-uniform trip count so the queue append below runs with all 32 lanes converged
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + (threadIdx.x & 31u);
+        const bool valid = i < n;
+        uint32_t p = 0, type = 0;
+        if (valid) {
+            p = q_in[i];
+            const float4 ro = pa.ray_o[p], rd = pa.ray_d[p];
+            RayHit h;
+            h.t = rd.w, h.u = h.v = 0.f;
+            traverse<false, COUNT>(sv, mk3(ro), mk3(rd), ro.w, h, &ctr);
+            int32_t inst = -1;
+            uint32_t prim = 0;
+            if (h.prim_slot != 0xffffffffu) {
+                const float4 *rec = reinterpret_cast<const float4 *>(sv.prims + h.prim_slot);
+                prim = __float_as_uint(__ldg(rec).w);
+                inst = (int32_t)__float_as_uint(__ldg(rec + 1).w);
+                type = (uint32_t)__ldg(&sv.instances[inst].mat_type) & 7u;
+            }
+            pa.hit_tuvp[p] = make_float4(h.t, h.u, h.v, __uint_as_float(prim));
+            pa.hit_inst[p] = inst;
+            if (!sort) type = 1;
+        }
+        __syncwarp();
+        const uint32_t pos = warp_append_keyed(mat_counts, type, valid);
+        if (valid) q_mat[(size_t)type * capacity + pos] = p;
+    }
+    if (COUNT) {
+        atomicAdd(&trav[0], (unsigned long long)ctr.nodes);
+        atomicAdd(&trav[1], (unsigned long long)ctr.prims);
+    }
+}
+
+// ---- shadow ------------------------------------------------------------------------------------------------
+template<bool COUNT>
+__global__ void __launch_bounds__(128) k_shadow(SceneView sv, PathArrays pa, const uint32_t *__restrict__ q_in, const uint32_t *__restrict__ n_in,
+                                                unsigned long long *__restrict__ trav) {
+    const uint32_t n = *n_in;
+    TraceCounters ctr{ 0, 0 };
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t p = q_in[i];
+        const float4 ro = pa.sh_o[p], rd = pa.sh_d[p];
+        RayHit h;
+        h.t = rd.w, h.u = h.v = 0.f;
+        if (!traverse<true, COUNT>(sv, mk3(ro), mk3(rd), ro.w, h, &ctr)) { // main.cu:127 `if (!occluded)`
+            const float4 c = pa.sh_c[p];
+            float4 r = pa.rad[p];
+            r.x += c.x, r.y += c.y, r.z += c.z;
+            pa.rad[p] = r;
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&trav[2], (unsigned long long)ctr.nodes);
+        atomicAdd(&trav[3], (unsigned long long)ctr.prims);
+    }
+}
+
+// ---- closest-hit program: Geometry::GetHitLocalGeometry, framework/render/geometry.h:60-100,176-180 ------------
+struct LocalGeometry {
+    float3 position, normal;
+    float2 texcoord;
+};
+__device__ __forceinline__ void hit_local_geometry(const DevInstance *in, uint32_t flags, float3 ro, float3 rd, float t, float bu, float bv,
+                                                   uint32_t prim, LocalGeometry &g) {
+    const float4 i0 = __ldg(&in->inv[0]), i1 = __ldg(&in->inv[1]), i2 = __ldg(&in->inv[2]);
+    g.texcoord = make_float2(0.f, 0.f); // defined: the reference leaves it untouched for meshes without uvs
+    if (flags & PB2_IF_SPHERE) {
+        g.position = ro + t * rd;
+        const float3 local_pos = xf_point(i0, i1, i2, g.position);
+        g.texcoord = sphere_texcoord(normalize(local_pos));
+        g.normal = normalize(xf_normal_t(i0, i1, i2, local_pos));
+    } else {
+        const float4 x0 = __ldg(&in->xf[0]), x1 = __ldg(&in->xf[1]), x2 = __ldg(&in->xf[2]);
+        const float *pos = in->pos, *nrm = in->nrm, *uv = in->uv;
+        const uint32_t *idx = in->idx + (size_t)prim * 3;
+        const uint32_t v0 = __ldg(idx), v1 = __ldg(idx + 1), v2 = __ldg(idx + 2);
+        auto ld3 = [](const float *a, uint32_t v) { return mk3(__ldg(a + (size_t)v * 3), __ldg(a + (size_t)v * 3 + 1), __ldg(a + (size_t)v * 3 + 2)); };
+        const float3 p0 = ld3(pos, v0), p1 = ld3(pos, v1), p2 = ld3(pos, v2);
+        const float w = 1.f - bu - bv;
+        g.position = xf_point(x0, x1, x2, w * p0 + bu * p1 + bv * p2);
+        float3 n;
+        if (flags & PB2_IF_HAS_NRM) n = w * ld3(nrm, v0) + bu * ld3(nrm, v1) + bv * ld3(nrm, v2);
+        else n = cross(p1 - p0, p2 - p0);
+        g.normal = normalize(xf_normal_t(i0, i1, i2, n));
+        if (flags & PB2_IF_HAS_UV) {
+            auto ld2 = [](const float *a, uint32_t v) { return make_float2(__ldg(a + (size_t)v * 2), __ldg(a + (size_t)v * 2 + 1)); };
+            g.texcoord = w * ld2(uv, v0) + bu * ld2(uv, v1) + bv * ld2(uv, v2);
+            if (flags & PB2_INST_FLIP_TEX) g.texcoord.y = 1.f - g.texcoord.y;
+        }
+    }
+    if (flags & PB2_INST_FLIP_NORMALS) g.normal *= -1.f;
+    if (dot(-rd, g.normal) < 0.f && (flags & PB2_IF_TWOSIDED)) g.normal = -g.normal;
+}
+
+// ---- shade -------------------------------------------------------------------------------------------------
+struct ShadeOut {
+    uint32_t *q_ext, *n_ext, *q_shadow, *n_shadow;
+    float *albedo, *normal, *test; // AOVs (may be null); written by the last frame of the batch only
+    uint32_t write_aov_frame;      // frame index (within the batch) whose primary hits write the AOVs; ~0u = none
+};
+
+// One path at one hit (or miss).  Returns bit 0: a shadow ray was written, bit 1: an extension ray was written.
+__device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathArrays &pa, const FrameParams &fp, const ShadeOut &out, uint32_t p) {
+    const float4 hit = pa.hit_tuvp[p];
+    const int32_t inst = pa.hit_inst[p];
+    const float4 ro4 = pa.ray_o[p], rd4 = pa.ray_d[p];
+    const float3 ray_o = mk3(ro4), ray_d = mk3(rd4);
+    const float4 thr4 = pa.thr[p];
+    float3 throughput = mk3(thr4);
+    const float bsdf_pdf = thr4.w;
+    const uint32_t st = pa.state[p];
+    uint32_t depth = st & 0xffffu;
+    const uint32_t sampled_type = st >> 16;
+    uint32_t rng = pa.rng[p];
+    float3 radiance = mk3(pa.rad[p]);
+    const uint32_t frame = p / fp.n_pixels, pixel = p - frame * fp.n_pixels;
+    const bool write_aov = depth == 0 && frame == out.write_aov_frame;
+
+    if (inst < 0) { // __miss__default, main.cu:199-215
+        float3 env_radiance = mk3(0.f);
+        float env_pdf = 0.f;
+        if (sv.env) emitter_eval(sv.env, ray_o + normalize(ray_d), mk3(0.f), make_float2(0.f, 0.f), ray_o, env_radiance, env_pdf);
+        if (depth == 0) {
+            if (write_aov) { // :100-104
+                if (out.albedo) out.albedo[pixel * 3] = 0.f, out.albedo[pixel * 3 + 1] = 0.f, out.albedo[pixel * 3 + 2] = 0.f;
+                if (out.normal) out.normal[pixel * 3] = 0.f, out.normal[pixel * 3 + 1] = 0.f, out.normal[pixel * 3 + 2] = 0.f;
+                if (out.test) out.test[pixel] = rng_next(rng);
+            }
+        } else if (sv.env) { // :168-172
+            const float mis = mis_weight(bsdf_pdf, env_pdf);
+            env_radiance *= throughput * mis;
+        }
+        radiance += env_radiance; // :188
+        pa.rad[p] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
+        return 0u;
+    }
+
+    // __closesthit__default, main.cu:220-234
+    const DevInstance *in = sv.instances + inst;
+    const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(&in->flags)); // flags, mat_type, emitter_offset, n_tris
+    const uint32_t flags = meta.x;
+    const uint32_t prim = __float_as_uint(hit.w);
+    LocalGeometry geo;
+    hit_local_geometry(in, flags, ray_o, ray_d, hit.x, hit.y, hit.z, prim, geo);
+    const int emitter_index = (int)meta.z >= 0 ? (int)meta.z + (int)prim : -1;
+    const LocalBsdf bsdf = get_local_bsdf(sv.materials + inst, geo.texcoord);
+
+    if (depth == 0) { // :90-104
+        if (emitter_index >= 0) radiance += emitter_radiance(sv.areas + emitter_index, geo.texcoord);
+        if (write_aov) {
+            const float3 a = local_albedo(bsdf);
+            if (out.albedo) out.albedo[pixel * 3] = a.x, out.albedo[pixel * 3 + 1] = a.y, out.albedo[pixel * 3 + 2] = a.z;
+            if (out.normal) out.normal[pixel * 3] = geo.normal.x, out.normal[pixel * 3 + 1] = geo.normal.y, out.normal[pixel * 3 + 2] = geo.normal.z;
+        }
+        const float test = rng_next(rng); // :104 — one draw per path whether or not the buffer exists
+        if (write_aov && out.test) out.test[pixel] = test;
+    } else if (emitter_index >= 0) { // :175-185
+        const DevEmitter *em = sv.areas + emitter_index;
+        float3 le;
+        float pdf;
+        emitter_eval(em, geo.position, geo.normal, geo.texcoord, ray_o, le, pdf);
+        if (!is_zero(pdf)) {
+            const float mis = (sampled_type & kLobeDelta) ? 1.f : mis_weight(bsdf_pdf, pdf * __ldg(&em->select_probability));
+            radiance += throughput * le * mis;
+        }
+    }
+
+    // ---- loop head, :106-114 ----
+    bool alive = true;
+    ++depth;
+    if (depth >= fp.max_depth) alive = false;
+    if (alive) {
+        const float rr = depth > 2 ? 0.95 : 1.0;
+        if (rng_next(rng) > rr) alive = false;
+        else throughput /= rr;
+    }
+    if (!alive) {
+        pa.rad[p] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
+        pa.rng[p] = rng;
+        return 0u;
+    }
+    const Onb frame_onb(geo.normal);
+    const float3 wo = frame_onb.to_local(-ray_d);
+    uint32_t emitted = 0;
+
+    // ---- direct light sampling, :117-144 ----
+    {
+        const float sel = rng_next(rng);
+        const float e0 = rng_next(rng), e1 = rng_next(rng);
+        const DevEmitter *em = select_emitter(sv.areas, sv.n_areas, sv.env, sel);
+        if (em) {
+            EmitSample es;
+            emitter_sample_direct(em, geo.position, geo.normal, frame_onb, make_float2(e0, e1), es);
+            if (es.pdf != 0.f) {
+                // the reference traces first and evaluates after; evaluating first lets rays whose
+                // contribution is zero anyway be skipped — same image, fewer rays
+                BsdfRec rec;
+                rec.wi = frame_onb.to_local(es.wi), rec.wo = wo;
+                bsdf_eval(bsdf, rec);
+                if (!is_zero(rec.f * es.pdf)) {
+                    const float NoL = dot(geo.normal, es.wi);
+                    if (NoL > 0.f) {
+                        const float mis = es.is_delta ? 1.f : mis_weight(es.pdf, rec.pdf);
+                        const float pdf_e = es.pdf * __ldg(&em->select_probability);
+                        const float3 contrib = throughput * es.radiance * rec.f * NoL * mis / pdf_e;
+                        pa.sh_o[p] = make_float4(geo.position.x, geo.position.y, geo.position.z, 0.0001f);
+                        pa.sh_d[p] = make_float4(es.wi.x, es.wi.y, es.wi.z, es.distance - 0.0001f);
+                        pa.sh_c[p] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                        emitted |= 1u;
+                    }
+                }
+            }
+        }
+    }
+    // ---- BSDF sampling, :146-166 ----
+    {
+        BsdfRec rec;
+        rec.wo = wo;
+        bsdf_sample(bsdf, rec, rng);
+        if (!(is_zero(rec.f * fabsf(rec.wi.z)) || is_zero(rec.pdf))) {
+            throughput *= rec.f * fabsf(rec.wi.z) / rec.pdf;
+            const float3 dir = frame_onb.to_world(rec.wi);
+            pa.ray_o[p] = make_float4(geo.position.x, geo.position.y, geo.position.z, 0.001f);
+            pa.ray_d[p] = make_float4(dir.x, dir.y, dir.z, 1e16f);
+            pa.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, rec.pdf);
+            pa.state[p] = depth | (rec.type << 16);
+            emitted |= 2u;
+        }
+    }
+    pa.rad[p] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
+    pa.rng[p] = rng;
+    return emitted;
+}
+
+__global__ void __launch_bounds__(128) k_shade(SceneView sv, PathArrays pa, FrameParams fp, const uint32_t *__restrict__ q_mat,
+                                               const uint32_t *__restrict__ mat_counts, uint32_t capacity, ShadeOut out) {
+    // queue t occupies the virtual index range [start_t, start_t + round_up(count_t, 32)): a warp never
+    // straddles two material types
+    uint32_t start[kNumTypes + 1];
+    start[0] = 0;
+#pragma unroll
+    for (int t = 0; t < kNumTypes; ++t) start[t + 1] = start[t] + ((mat_counts[t] + 31u) & ~31u);
+    const uint32_t total = start[kNumTypes];
+
+    for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total; vi += gridDim.x * blockDim.x) { // total % 32 == 0: warp-uniform
+        int t = 0;
+#pragma unroll
+        for (int k = 1; k < kNumTypes; ++k) t += vi >= start[k] ? 1 : 0;
+        const uint32_t local = vi - start[t];
+        uint32_t emitted = 0, p = 0;
+        if (local < mat_counts[t]) {
+            p = q_mat[(size_t)t * capacity + local];
+            emitted = shade_path(sv, pa, fp, out, p);
+        }
+        __syncwarp();
+        const uint32_t ps = warp_append(out.n_shadow, emitted & 1u);
+        if (emitted & 1u) out.q_shadow[ps] = p;
+        const uint32_t pe = warp_append(out.n_ext, emitted & 2u);
+        if (emitted & 2u) out.q_ext[pe] = p;
+    }
+}
+
+// adds one batch's per-round queue sizes into the 64-bit ray totals: [0] closest, [1] shadow
+__global__ void k_collect_counts(const uint32_t *__restrict__ counters, uint32_t rounds, unsigned long long *__restrict__ totals) {
+    unsigned long long c = 0, sh = 0;
+    for (uint32_t r = threadIdx.x; r < rounds; r += blockDim.x) {
+        c += counters[r * kCtrPerRound + CTR_EXT];
+        if (r + 1 < rounds) sh += counters[r * kCtrPerRound + CTR_SHADOW];
+    }
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o), sh += __shfl_xor_sync(0xffffffffu, sh, o);
+    if (threadIdx.x == 0) totals[0] += c, totals[1] += sh;
+}
+
+// ---- accumulate: main.cu:190-196 ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_accumulate(const float4 *__restrict__ rad, uint32_t n_pixels, uint32_t frames, uint32_t mode, uint32_t sample_cnt0,
+                                                    float4 *__restrict__ accum, float4 *__restrict__ frame_buf) {
+    for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < n_pixels; px += gridDim.x * blockDim.x) {
+        float3 acc = (mode != 0 && (sample_cnt0 > 0 || mode == 2)) ? mk3(accum[px]) : mk3(0.f);
+        float w = mode == 2 ? accum[px].w : 1.f;
+        for (uint32_t f = 0; f < frames; ++f) {
+            const float3 r = mk3(rad[(size_t)f * n_pixels + px]);
+            if (mode == 2) { // plain sum for sample-sharded multi-GPU rendering
+                acc += r;
+                w += 1.f;
+            } else {
+                const uint32_t sample_cnt = mode == 1 ? sample_cnt0 + f : 0u;
+                if (mode == 1 && sample_cnt > 0) {
+                    const float t = 1.f / (sample_cnt + 1.f);
+                    acc = lerp3(acc, r, t);
+                } else {
+                    acc = r;
+                }
+            }
+        }
+        const float4 o = make_float4(acc.x, acc.y, acc.z, w);
+        accum[px] = o;
+        if (frame_buf && mode != 2) frame_buf[px] = o;
+    }
+}
+__global__ void k_finalize_sum(const float4 *__restrict__ sum, float4 *__restrict__ frame, uint64_t n, float inv_spp) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const float4 s = sum[i];
+        frame[i] = make_float4(s.x * inv_spp, s.y * inv_spp, s.z * inv_spp, 1.f);
+    }
+}
+}// namespace
+
+void finalize_sum(Scene &s, const float4 *sum, float4 *frame, uint64_t n, uint32_t spp) {
+    if (!n) return;
+    k_finalize_sum<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, s.stream>>>(sum, frame, n, 1.f / (float)spp);
+    PB2_LAUNCH_CHECK();
+}
+
+void render(Scene &s, const pb2_launch_params &lp) {
+    if (!s.bvh_valid) throw std::runtime_error("pb2_render: call pb2_bvh_build first");
+    if (!lp.accum_buffer || !lp.width || !lp.height) throw std::runtime_error("pb2_render: accum_buffer / width / height missing");
+    if (lp.max_depth > 0xffffu) throw std::runtime_error("pb2_render: max_depth too large");
+    s.upload_tables();
+    if (!s.wf) s.wf = new Wavefront();
+    Wavefront &wf = *s.wf;
+    cudaStream_t st = s.stream;
+
+    const uint32_t n_pixels = lp.width * lp.height;
+    const uint32_t n_frames = std::max(1u, lp.n_frames);
+    const uint64_t target = s.paths_in_flight ? s.paths_in_flight : (4ull << 20);
+    const uint32_t S = (uint32_t)std::min<uint64_t>(n_frames, std::max<uint64_t>(1, target / n_pixels));
+    const uint32_t rounds = std::max(1u, lp.max_depth);
+    wf.ensure((uint64_t)S * n_pixels, rounds + 1);
+    if ((uint64_t)S * n_pixels >= 0xffffffffull) throw std::runtime_error("pb2_render: too many paths in flight");
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const SceneView sv = s.view();
+    PathArrays pa{ wf.ray_o.ptr, wf.ray_d.ptr, wf.hit_tuvp.ptr, wf.thr.ptr, wf.rad.ptr, wf.sh_o.ptr, wf.sh_d.ptr, wf.sh_c.ptr,
+                   wf.hit_inst.ptr, wf.rng.ptr, wf.state.ptr };
+
+    for (auto &e : wf.events) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
+    wf.events.clear();
+    wf.launches = 0, wf.batches = 0, wf.rounds_used = rounds;
+    auto stage_begin = [&](int stage) {
+        if (!s.profiling) return;
+        Wavefront::Ev e{ stage, nullptr, nullptr };
+        cudaEventCreate(&e.a), cudaEventCreate(&e.b);
+        cudaEventRecord(e.a, st);
+        wf.events.push_back(e);
+    };
+    auto stage_end = [&]() {
+        if (s.profiling) cudaEventRecord(wf.events.back().b, st);
+    };
+    if (s.counting) wf.trav_counters.zero(st);
+    wf.ray_totals.zero(st);
+    PB2_CUDA(cudaEventRecord(wf.t0, st));
+
+    uint32_t sample_cnt = lp.sample_cnt;
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += S) {
+        const uint32_t frames = std::min(S, n_frames - f0);
+        const uint32_t n_paths = frames * n_pixels;
+        FrameParams fp{ lp.width, lp.height, n_pixels, lp.max_depth, lp.random_seed + f0 * (lp.seed_stride ? lp.seed_stride : 1u),
+                        lp.seed_stride ? lp.seed_stride : 1u, frames };
+        const unsigned grid_stream = (unsigned)std::min<uint64_t>((n_paths + 255) / 256, (uint64_t)sms * 8);
+        const unsigned grid_trace = (unsigned)std::min<uint64_t>((n_paths + 127) / 128, (uint64_t)sms * 16);
+        const unsigned grid_shade = (unsigned)std::min<uint64_t>((n_paths + kNumTypes * 32 + 127) / 128, (uint64_t)sms * 12);
+
+        PB2_CUDA(cudaMemsetAsync(wf.counters.ptr, 0, wf.counters.bytes(), st));
+        stage_begin(0);
+        k_generate<<<grid_stream, 256, 0, st>>>(pa, fp, s.cam, wf.q_ext[0].ptr, n_paths);
+        PB2_LAUNCH_CHECK();
+        stage_end();
+        PB2_CUDA(cudaMemcpyAsync(wf.counters.ptr + CTR_EXT, &n_paths, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        ++wf.launches;
+
+        const bool last_batch = f0 + frames >= n_frames;
+        for (uint32_t r = 0; r < rounds; ++r) {
+            uint32_t *ctr = wf.counters.ptr + (size_t)r * kCtrPerRound, *ctr_next = ctr + kCtrPerRound;
+            uint32_t *q_in = wf.q_ext[r & 1].ptr, *q_out = wf.q_ext[(r + 1) & 1].ptr;
+            stage_begin(1);
+            if (s.counting)
+                k_extend<true><<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity,
+                                                            s.sort_by_material ? 1 : 0, wf.trav_counters.ptr);
+            else
+                k_extend<false><<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity,
+                                                             s.sort_by_material ? 1 : 0, nullptr);
+            PB2_LAUNCH_CHECK();
+            stage_end();
+            ShadeOut so{ q_out, ctr_next + CTR_EXT, wf.q_shadow.ptr, ctr + CTR_SHADOW, (float *)lp.albedo_buffer, (float *)lp.normal_buffer,
+                         (float *)lp.test_buffer, last_batch ? frames - 1 : ~0u };
+            stage_begin(2);
+            k_shade<<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
+            PB2_LAUNCH_CHECK();
+            stage_end();
+            wf.launches += 2;
+            if (r + 1 < rounds) { // the last round cannot emit rays (depth >= max_depth)
+                stage_begin(3);
+                if (s.counting) k_shadow<true><<<grid_trace, 128, 0, st>>>(sv, pa, wf.q_shadow.ptr, ctr + CTR_SHADOW, wf.trav_counters.ptr);
+                else k_shadow<false><<<grid_trace, 128, 0, st>>>(sv, pa, wf.q_shadow.ptr, ctr + CTR_SHADOW, nullptr);
+                PB2_LAUNCH_CHECK();
+                stage_end();
+                ++wf.launches;
+            }
+        }
+        stage_begin(4);
+        k_accumulate<<<(unsigned)std::min<uint64_t>((n_pixels + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>(
+            wf.rad.ptr, n_pixels, frames, lp.accumulate, sample_cnt, (float4 *)lp.accum_buffer, (float4 *)lp.frame_buffer);
+        PB2_LAUNCH_CHECK();
+        stage_end();
+        ++wf.launches;
+        if (lp.accumulate == 1) sample_cnt += frames;
+        k_collect_counts<<<1, 32, 0, st>>>(wf.counters.ptr, rounds, wf.ray_totals.ptr);
+        PB2_LAUNCH_CHECK();
+        ++wf.batches;
+    }
+    PB2_CUDA(cudaEventRecord(wf.t1, st));
+    wf.stats_pending = true;
+}
+
+void collect_render_stats(Scene &s) {
+    if (!s.wf || !s.wf->stats_pending) return;
+    Wavefront &wf = *s.wf;
+    PB2_CUDA(cudaStreamSynchronize(s.stream));
+    pb2_render_stats rs{};
+    unsigned long long totals[2];
+    PB2_CUDA(cudaMemcpy(totals, wf.ray_totals.ptr, sizeof totals, cudaMemcpyDeviceToHost));
+    rs.closest_rays = totals[0], rs.shadow_rays = totals[1];
+    rs.kernel_launches = wf.launches;
+    PB2_CUDA(cudaEventElapsedTime(&rs.total_ms, wf.t0, wf.t1));
+    for (auto &e : wf.events) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        (e.stage == 0 ? rs.generate_ms : e.stage == 1 ? rs.extend_ms : e.stage == 2 ? rs.shade_ms : e.stage == 3 ? rs.shadow_ms : rs.accumulate_ms) += ms;
+    }
+    if (s.counting) {
+        unsigned long long h[4];
+        PB2_CUDA(cudaMemcpy(h, wf.trav_counters.ptr, sizeof h, cudaMemcpyDeviceToHost));
+        rs.nodes_visited = h[0] + h[2], rs.prims_tested = h[1] + h[3];
+    }
+    s.render_stats = rs;
+    wf.stats_pending = false;
+}
+}// namespace pb2

@@ -116,6 +116,7 @@ def _declare(lib):
     lib.orc_get_area_emitters.argtypes = [C.c_void_p, P(Emitter)]
     lib.orc_get_env_emitter.argtypes = [C.c_void_p, P(Emitter)]
     lib.orc_num_instances.argtypes = [C.c_void_p]
+    lib.orc_get_instance_xform.argtypes = [C.c_void_p, C.c_int, P(f32)]
     lib.orc_num_triangles.argtypes = [C.c_void_p]
     lib.orc_num_triangles.restype = C.c_uint64
     lib.orc_trace_closest.argtypes = [C.c_void_p, P(f32), C.c_uint64, C.c_void_p, C.c_int, C.c_int, P(C.c_uint64)]
@@ -288,6 +289,11 @@ class OracleScene:
         fov = f32()
         self.lib.orc_get_camera(self.h, fp(s2c), fp(c2w), C.byref(fov))
         return s2c.reshape(4, 4), c2w.reshape(4, 4), fov.value
+
+    def instance_xform(self, i):
+        m = np.zeros(16, np.float32)
+        self.lib.orc_get_instance_xform(self.h, i, fp(m))
+        return m.reshape(4, 4)
 
     def area_emitters(self):
         n = self.lib.orc_num_area_emitters(self.h)

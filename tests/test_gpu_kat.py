@@ -1,0 +1,185 @@
+"""-m gpu: every device-side restatement (RNG, sampling warps, frames, Fresnel, GGX, textures, the seven
+BSDFs, emitters, emitter selection) against the oracle on the same seeded grids, through pb2_kat.
+
+Tolerances: integer work (RNG state/draws, lobe tags, selection indices) is bit-exact.  fp32 work is
+compared with rtol 2e-5 / atol 1e-6: the device build contracts a*b+c into FMAs and uses CUDA's
+sinf/cosf/atan2f/acosf (<= 2 ulp), the oracle is an x86 build with -ffp-contract=off and glibc libm.
+Where a formula divides by a vanishing quantity (grazing angles) the comparison is relative to the
+magnitude of the oracle value."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import kat
+import orc
+from pupiloptixlab_b200 import pb2
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+RTOL, ATOL = 2e-5, 1e-6
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    pb2.init(0)
+
+
+@pytest.fixture(scope="module")
+def ref(port_lib):
+    return kat.run(port_lib)
+
+
+def close(a, b, rtol=RTOL, atol=ATOL):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    ok = np.isclose(a, b, rtol=rtol, atol=atol, equal_nan=True) | (np.isinf(a) & np.isinf(b) & (np.sign(a) == np.sign(b)))
+    assert ok.all(), f"{np.count_nonzero(~ok)} mismatches, worst: gpu={a[~ok][:4]} ref={b[~ok][:4]}"
+
+
+def test_rng_bit_exact(ref):
+    cases = np.array([[4, 0, 0], [4, 1, 0], [4, 12345, 7], [4, 262143, 63], [4, 2073599, 4095], [4, 0xFFFFFFFF, 0xFFFFFFFF]], np.uint32)
+    out = np.zeros((len(cases), 8), F)
+    pb2.kat("rng", cases, None, None, len(cases), out)
+    assert np.array_equal(out[:, 0].view(np.uint32), ref["rng_state"])
+    assert np.array_equal(out[:, 1:], ref["rng_stream"][:, :7])
+
+
+def test_warps(ref):
+    U = ref["warp_in"]
+    out = np.zeros((len(U), 12), F)
+    pb2.kat("warp", U, None, None, len(U), out)
+    for k, name in enumerate(["tri", "sphere", "coshemi", "unihemi"]):
+        close(out[:, 3 * k:3 * k + 3], ref["warp_" + name], atol=2e-6)
+
+
+def test_frames(ref):
+    inp = np.concatenate([ref["frame_v"], ref["frame_n"]], 1).astype(F)
+    out = np.zeros((len(inp), 8), F)
+    pb2.kat("frame", inp, None, None, len(inp), out)
+    close(out[:, 0:3], ref["frame_local"], atol=2e-6)
+    close(out[:, 3:6], ref["frame_world"], atol=2e-6)
+    close(out[:, 6:8], ref["sphere_uv"], atol=2e-6)
+
+
+def test_fresnel(ref):
+    cos, etas = ref["fresnel_cos"], ref["fresnel_eta"]
+    eta3, k3 = [0.200438, 0.924033, 1.10221], [3.91295, 2.45285, 2.14219]
+    for i, e in enumerate(etas):
+        inp = np.array([[e, c, *eta3, *k3] for c in cos], F)
+        out = np.zeros((len(cos), 8), F)
+        pb2.kat("fresnel", inp, None, None, len(cos), out)
+        close(out[:, 0], ref["fresnel_dielectric"][i], atol=2e-6)
+        close(out[:, 1], ref["fresnel_cos_t"][i], atol=2e-6)
+        close(out[:, 2:5], ref["fresnel_conductor"], atol=2e-6)
+
+
+def test_ggx(ref):
+    WO, WI, WH, xi = ref["ggx_wo"], ref["ggx_wi"], ref["ggx_wh"], ref["ggx_xi"]
+    for a, al in enumerate(ref["ggx_alpha"]):
+        inp = np.concatenate([WI, WO, WH, np.full((len(WO), 1), al, F), xi], 1).astype(F)
+        out = np.zeros((len(WO), 8), F)
+        pb2.kat("ggx", inp, None, None, len(WO), out)
+        close(out[:, 0:4], ref["ggx_dgp"][a], rtol=5e-5)
+        close(out[:, 4:7], ref["ggx_sample"][a], atol=5e-6)
+
+
+def test_textures(ref):
+    from pupiloptixlab_b200.scenes import Tex
+    UV = ref["tex_uv"]
+    t = pb2.Texture()
+    t.type = pb2.TEX_CHECKERBOARD
+    t.a[:], t.b[:] = (0.8, 0.7, 0.6), (0.1, 0.2, 0.3)
+    t.r0[:], t.r1[:] = (5, 0, 0, 0), (0, 3, 0, 0)
+    arr = (pb2.Texture * len(UV))(*[t] * len(UV))
+    out = np.zeros((len(UV), 4), F)
+    pb2.kat("texture", arr, UV, None, len(UV), out)
+    # a checker lookup is a discrete choice: positions within 1e-6 of a cell edge may legitimately flip
+    fx, fy = (UV[:, 0] * 5) % 1.0, (UV[:, 1] * 3) % 1.0
+    edge = (np.abs(fx - 0.5) < 1e-5) | (np.abs(fy - 0.5) < 1e-5) | (fx < 1e-5) | (fy < 1e-5) | (fx > 1 - 1e-5) | (fy > 1 - 1e-5)
+    assert np.array_equal(out[~edge, :3], ref["tex_checker"][~edge])
+
+
+def _kat_bsdf(b: orc.LocalBsdf) -> pb2.KatBsdf:
+    k = pb2.KatBsdf()
+    k.type, k.alpha, k.eta, k.int_fdr, k.specular_sampling_weight, k.nonlinear = b.type, b.alpha, b.eta, b.int_fdr, b.specular_sampling_weight, b.nonlinear
+    name = {v: n for n, v in orc.MAT.items()}[b.type]
+    if name == "diffuse":
+        k.c0[:] = b.reflectance
+    elif name in ("dielectric", "roughdielectric"):
+        k.c0[:], k.c1[:] = b.specular_reflectance, b.specular_transmittance
+    elif name in ("conductor", "roughconductor"):
+        k.c0[:], k.c1[:], k.c2[:] = b.specular_reflectance, b.eta3, b.k3
+    else:
+        k.c0[:], k.c1[:] = b.reflectance, b.specular_reflectance
+    return k
+
+
+def test_bsdfs(ref):
+    mats = kat.local_bsdfs()
+    WO, WI, rng_in = ref["bsdf_wo"], ref["bsdf_wi"], ref["bsdf_rng_in"]
+    n = len(WO)
+    worst = 0
+    for m, b in enumerate(mats):
+        arr = (pb2.KatBsdf * n)(*[_kat_bsdf(b)] * n)
+        inp = np.zeros((n, 8), F)
+        inp[:, 0:3], inp[:, 3:6] = WO, WI
+        inp[:, 6] = rng_in.view(F)
+        out = np.zeros((n, 16), F)
+        pb2.kat("bsdf", arr, inp, None, n, out)
+        # integer-exact: RNG consumption and the sampled lobe tag — except where the lobe choice compares a
+        # draw with a computed probability that differs in the last bit (none on this grid)
+        assert np.array_equal(out[:, 8].view(np.uint32), ref["bsdf_sample_rng"][m]), f"material {m}: RNG consumption differs"
+        same_lobe = out[:, 7].view(np.uint32) == ref["bsdf_sample_type"][m]
+        assert same_lobe.all(), f"material {m}: lobe tags differ on {np.count_nonzero(~same_lobe)} samples"
+        s_ref, e_ref = ref["bsdf_sample"][m], ref["bsdf_eval"][m]
+        # f and pdf blow up at grazing angles (divisions by wi.z*wo.z): compare relative to magnitude
+        close(out[:, 0:3], s_ref[:, 0:3], atol=5e-6)
+        close(out[:, 3:7], s_ref[:, 3:7], rtol=2e-4, atol=1e-6)
+        close(out[:, 9:13], e_ref, rtol=2e-4, atol=1e-6)
+        worst = max(worst, float(np.nanmax(np.abs(out[:, 3:7] - s_ref[:, 3:7]) / (np.abs(s_ref[:, 3:7]) + 1e-3))))
+    print("worst relative f/pdf difference:", worst)
+
+
+def _pb2_emitter(e: orc.Emitter) -> pb2.Emitter:
+    p = pb2.Emitter()
+    p.type, p.weight, p.select_probability, p.area = e.type, e.weight, e.select_probability, e.area
+    p.radiance.type = e.radiance.type
+    p.radiance.a[:], p.radiance.b[:] = e.radiance.a, e.radiance.b
+    p.radiance.r0[:], p.radiance.r1[:] = e.radiance.to_uv[0:4], e.radiance.to_uv[4:8]
+    for k in range(3):
+        p.pos[k][:], p.nrm[k][:], p.uv[k][:] = e.pos[k], e.nrm[k], e.uv[k]
+    p.center[:], p.radius = e.center, e.radius
+    return p
+
+
+def test_emitters(ref):
+    ems = kat.emitters()
+    HP, HN, XI = ref["emit_hit_pos"], ref["emit_hit_n"], ref["emit_xi"]
+    n = len(HP)
+    for k, e in enumerate(ems):
+        arr = (pb2.Emitter * n)(*[_pb2_emitter(e)] * n)
+        in1 = np.concatenate([HP, HN, XI], 1).astype(F)
+        sd = ref["emit_sample"][k]  # radiance wi pos normal distance pdf is_delta
+        in2 = np.zeros((n, 12), F)
+        in2[:, 0:3], in2[:, 3:6], in2[:, 6:8], in2[:, 8:11] = sd[:, 6:9], sd[:, 9:12], XI, HP
+        out = np.zeros((n, 16), F)
+        pb2.kat("emitter", arr, in1, in2, n, out)
+        if e.radiance.type == orc.TEX_RGB:
+            close(out[:, 0:3], sd[:, 0:3])
+        close(out[:, 3:6], sd[:, 3:6], atol=5e-6)
+        close(out[:, 6], sd[:, 12], rtol=1e-4)
+        close(out[:, 7], sd[:, 13], rtol=2e-4)
+        if e.radiance.type == orc.TEX_RGB:
+            close(out[:, 8:12], ref["emit_eval"][k], rtol=2e-4)
+        else:
+            close(out[:, 11], ref["emit_eval"][k][:, 3], rtol=2e-4)
+
+
+def test_select_emitter(ref):
+    ems = kat.emitters()[:3]
+    arr = (pb2.Emitter * 3)(*[_pb2_emitter(e) for e in ems])
+    ps = ref["select_p"]
+    for has_env, key in ((1, "select_env"), (0, "select_noenv")):
+        out = np.zeros(len(ps), np.int32)
+        pb2.kat("select", arr, ps, np.array([3, has_env], np.uint32), len(ps), out)
+        assert np.array_equal(out, ref[key])
