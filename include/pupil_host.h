@@ -1,0 +1,75 @@
+/* pupil_host — C entry points of the host library (libpupil_host.so), for callers that cannot include the
+ * C++ surface in pupiloptixlab_b200/host/ (Pupil::System, Pupil::pt::PTPass, Pupil::world::World ...):
+ * the Python tests, bench.py and scripted use.  Everything here is a thin veneer over that C++ surface —
+ * the same calls example/path_tracer/main.cpp makes (System::Init / AddPass / SetScene / Run) — which in
+ * turn drives the CUDA back end only through include/pb2.h.
+ *
+ * All functions return 0 on success; pupil_last_error() describes the last failure.  Not thread-safe:
+ * one caller thread, like the reference's render loop. */
+#ifndef PUPIL_HOST_H
+#define PUPIL_HOST_H
+#include "pb2.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* System::Init(false) on a CUDA device + one PTPass registered with AddPass (example/path_tracer/main.cpp:5-12) */
+int pupil_init(int device);
+/* System::Destroy (main.cpp:20) */
+int pupil_shutdown(void);
+const char *pupil_last_error(void);
+/* 0 silent, 1 warnings (default), 2 info */
+int pupil_set_log_level(int level);
+
+/* System::SetScene(path) (main.cpp:13-16; framework/system/system.cpp:136-173) */
+int pupil_load_scene_xml(const char *path);
+/* same dialect from memory; root_dir resolves relative file names (may be NULL) */
+int pupil_load_scene_xml_string(const char *xml, const char *root_dir);
+/* host-only variants (no CUDA device needed): parse + World::LoadScene precompute (camera matrices, material
+ * precompute, emitter table), for inspection through the getters below; nothing is uploaded or rendered */
+int pupil_parse_scene_xml(const char *path);
+int pupil_parse_scene_xml_string(const char *xml, const char *root_dir);
+/* make a triangle mesh available to scene files as <string name="filename" value="mem:KEY"/>
+ * (ShapeManager::LoadMeshShape without the text round trip; arrays are copied; nrm / uv may be NULL) */
+int pupil_register_mesh(const char *key, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t n_vertices,
+                        uint32_t n_triangles);
+/* forget every cached shape (ShapeManager::Clear) */
+int pupil_clear_shapes(void);
+
+/* PTPass knobs: max_depth <= 0 keeps the scene's integrator.max_depth; accumulate = the inspector checkbox
+ * (pt_pass.cpp:256-268); frames_per_run = frames executed per PTPass::OnRun; first_seed / seed_stride = the
+ * random_seed sequence (reference: 0, 1); sum_mode != 0 accumulates plain sums (multi-GPU shards). */
+int pupil_pass_config(int max_depth, int accumulate, uint32_t frames_per_run, uint32_t first_seed, uint32_t seed_stride, int sum_mode);
+/* System::Run() for n_pass_runs iterations of the pass list (headless: returns instead of looping forever) */
+int pupil_run(uint64_t n_pass_runs);
+/* frames (samples per pixel) accumulated so far and the next random_seed */
+int pupil_pass_state(uint32_t *sample_cnt, uint32_t *random_seed);
+
+/* BufferManager::GetBuffer(name): "final result", "pt accum buffer", "albedo", "normal", "test" */
+int pupil_buffer_info(const char *name, void **device_ptr, uint32_t *width, uint32_t *height, uint32_t *stride_in_byte);
+int pupil_buffer_download(const char *name, void *host, uint64_t bytes);
+int pupil_buffer_upload(const char *name, const void *host, uint64_t bytes);
+
+/* introspection (parity tests): what World computed from the scene */
+int pupil_get_film(uint32_t *width, uint32_t *height, uint32_t *max_depth);
+int pupil_get_camera(float sample_to_camera[16], float camera_to_world[16], float *fov_y);
+int pupil_num_instances(void);
+int pupil_get_instance(uint32_t index, float xform[16], pb2_material *material, int32_t *emitter_offset, uint32_t *flags, uint32_t *n_prims,
+                       int32_t *is_sphere);
+int pupil_num_area_emitters(void);
+int pupil_get_emitters(pb2_emitter *areas, pb2_emitter *env, int32_t *has_env);
+/* World::GetSceneHandle(): the pb2 scene (BVH built, camera and emitters uploaded) for pb2_trace_* etc. */
+int pupil_scene_handle(pb2_scene **scene);
+int pupil_set_bvh_builder(int builder);
+int pupil_build_stats(pb2_build_stats *stats);
+int pupil_render_stats(pb2_render_stats *stats);
+/* camera edits through CameraHelper (framework/world/camera.cpp): mark the pass dirty like the GUI does */
+int pupil_camera_move(float dx, float dy, float dz);
+int pupil_camera_rotate(float delta_x, float delta_y);
+int pupil_camera_set_fov(float fov_y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -14,6 +14,9 @@
  * (closed source).  The contract restated here is geometric: nearest hit in (tmin, tmax) of the
  * exact primitive set, fp32 Moeller-Trumbore on world-space triangles and an analytic unit
  * sphere in object space; exact-t ties resolve to the lowest (instance, primitive).
+ * The intersection arithmetic is written with EXPLICIT fused multiply-adds (ix_* below): fmaf is
+ * exactly rounded on every IEEE machine, so the CUDA kernels, which spell out the same sequence with
+ * __fmaf_rn / __fmul_rn, produce bit-identical t, u, v.
  */
 #ifndef ORC_RENDER_H
 #define ORC_RENDER_H
@@ -155,7 +158,7 @@ struct Scene {
                 f3 p[3];
                 for (int k = 0; k < 3; ++k) {
                     uint32_t vi = md.idx[f * 3 + k];
-                    p[k] = obj_to_world_point(f3{ md.pos[vi * 3], md.pos[vi * 3 + 1], md.pos[vi * 3 + 2] }, in.xf);
+                    p[k] = ix_point(f3{ md.pos[vi * 3], md.pos[vi * 3 + 1], md.pos[vi * 3 + 2] }, in.xf.e);
                 }
                 tris.push_back(WorldTri{ p[0], p[1] - p[0], p[2] - p[0], (int)ii, (int)f });
             }
@@ -178,18 +181,28 @@ struct Scene {
     }
 
     // ---------- intersection ----------
+    // fixed-rounding building blocks (same sequence as csrc/traverse.cuh)
+    static float ix_dot(f3 a, f3 b) { return fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)); }
+    static f3 ix_cross(f3 a, f3 b) { return f3{ fmaf(a.y, b.z, -(a.z * b.y)), fmaf(a.z, b.x, -(a.x * b.z)), fmaf(a.x, b.y, -(a.y * b.x)) }; }
+    static f3 ix_point(f3 p, const float *m) { // rows of a 3x4 affine matrix
+        return f3{ fmaf(m[2], p.z, fmaf(m[1], p.y, fmaf(m[0], p.x, m[3]))), fmaf(m[6], p.z, fmaf(m[5], p.y, fmaf(m[4], p.x, m[7]))),
+                   fmaf(m[10], p.z, fmaf(m[9], p.y, fmaf(m[8], p.x, m[11]))) };
+    }
+    static f3 ix_vector(f3 v, const float *m) {
+        return f3{ fmaf(m[2], v.z, fmaf(m[1], v.y, m[0] * v.x)), fmaf(m[6], v.z, fmaf(m[5], v.y, m[4] * v.x)), fmaf(m[10], v.z, fmaf(m[9], v.y, m[8] * v.x)) };
+    }
     static bool hit_tri(const WorldTri &t, f3 o, f3 d, float tmin, float tmax, float &th, float &uh, float &vh) {
-        f3 pvec = cross(d, t.e2);
-        float det = dot(t.e1, pvec);
+        f3 pvec = ix_cross(d, t.e2);
+        float det = ix_dot(t.e1, pvec);
         if (det == 0.f) return false;
         float inv = 1.f / det;
         f3 tvec = o - t.v0;
-        float u = dot(tvec, pvec) * inv;
+        float u = ix_dot(tvec, pvec) * inv;
         if (u < 0.f || u > 1.f) return false;
-        f3 qvec = cross(tvec, t.e1);
-        float v = dot(d, qvec) * inv;
+        f3 qvec = ix_cross(tvec, t.e1);
+        float v = ix_dot(d, qvec) * inv;
         if (v < 0.f || u + v > 1.f) return false;
-        float tt = dot(t.e2, qvec) * inv;
+        float tt = ix_dot(t.e2, qvec) * inv;
         if (!(tt > tmin && tt < tmax)) return false;
         th = tt, uh = u, vh = v;
         return true;
@@ -198,9 +211,9 @@ struct Scene {
     // instance transform and NOT renormalised, so t is shared between the two spaces.
     bool hit_sphere(const WorldSphere &s, f3 o, f3 d, float tmin, float tmax, float &th) const {
         const Instance &in = instances[s.inst];
-        f3 oo = obj_to_world_point(o, in.inv), dd = obj_to_world_vector(d, in.inv);
-        float a = dot(dd, dd), b = dot(oo, dd), c = dot(oo, oo) - 1.f;
-        float disc = b * b - a * c;
+        f3 oo = ix_point(o, in.inv.e), dd = ix_vector(d, in.inv.e);
+        float a = ix_dot(dd, dd), b = ix_dot(oo, dd), c = ix_dot(oo, oo) - 1.f;
+        float disc = fmaf(b, b, -(a * c));
         if (!(disc >= 0.f) || a == 0.f) return false;
         float sq = sqrtf(disc);
         float t0 = (-b - sq) / a, t1 = (-b + sq) / a;

@@ -62,27 +62,23 @@ def build_pb2(force: bool = False) -> Path:
     return out
 
 
-def build_host(force: bool = False) -> Path | None:
-    srcs = sorted(HOST.glob("*.cpp"))
-    if not srcs:
-        return None
+def build_host(force: bool = False) -> Path:
+    """libpupil_host.so (the C++ host surface + its C entry points) and the headless path_tracer executable."""
     BUILD.mkdir(exist_ok=True)
-    out = BUILD / "libpupil_host.so"
+    out, exe = BUILD / "libpupil_host.so", BUILD / "path_tracer"
+    lib_srcs = sorted(p for p in HOST.glob("*.cpp") if p.name != "main.cpp")
     hdrs = sorted(HOST.glob("*.h")) + sorted((ROOT / "include").glob("*.h"))
-    if force or _newer(out, [*srcs, *hdrs]):
-        _run([CXX, "-O2", "-std=c++20", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unused-function", f"-I{ROOT / 'include'}", f"-I{HOST}",
-              *map(str, srcs), "-o", str(out), f"-L{BUILD}", "-lpb2", f"-Wl,-rpath,$ORIGIN"])
+    common = [CXX, "-O2", "-std=c++20", "-fPIC", "-pthread", "-Wall", "-Wno-unused-function", f"-I{ROOT / 'include'}", f"-I{HOST}"]
+    if force or _newer(out, [*lib_srcs, *hdrs]):
+        _run([*common, "-shared", *map(str, lib_srcs), "-o", str(out), f"-L{BUILD}", "-lpb2", "-Wl,-rpath,$ORIGIN"])
+    if force or _newer(exe, [HOST / "main.cpp", out, *hdrs]):
+        _run([*common, str(HOST / "main.cpp"), "-o", str(exe), f"-L{BUILD}", "-lpupil_host", "-lpb2", "-Wl,-rpath,$ORIGIN"])
     return out
-
-
-def build_oracle() -> None:
-    subprocess.run(["make", "-C", str(ROOT / "oracle"), "all"], check=True, capture_output=True)
 
 
 def build_all(force: bool = False) -> None:
     build_pb2(force)
     build_host(force)
-    build_oracle()
 
 
 if __name__ == "__main__":

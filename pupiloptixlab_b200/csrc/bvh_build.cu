@@ -14,6 +14,7 @@
 //   5 collapse        breadth-first: binary subtree -> up to 8 children by largest-area expansion,
 //                     octant slot assignment, quantisation, leaf primitive copy
 #include "scene.cuh"
+#include "traverse.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
 
@@ -74,11 +75,12 @@ __global__ void k_emit_prims(const DevInstance *__restrict__ inst, const uint32_
             r.e2 = make_float4(0.f, 0.f, 0.f, __uint_as_float(1u));
         } else {
             const uint32_t i0 = in.idx[prim * 3], i1 = in.idx[prim * 3 + 1], i2 = in.idx[prim * 3 + 2];
-            float3 p0 = xf_point(in.xf[0], in.xf[1], in.xf[2], mk3(in.pos[i0 * 3], in.pos[i0 * 3 + 1], in.pos[i0 * 3 + 2]));
-            float3 p1 = xf_point(in.xf[0], in.xf[1], in.xf[2], mk3(in.pos[i1 * 3], in.pos[i1 * 3 + 1], in.pos[i1 * 3 + 2]));
-            float3 p2 = xf_point(in.xf[0], in.xf[1], in.xf[2], mk3(in.pos[i2 * 3], in.pos[i2 * 3 + 1], in.pos[i2 * 3 + 2]));
+            // ix_*: the fixed-rounding sequence of traverse.cuh, so the world-space record is reproducible bit for bit
+            float3 p0 = ix_point(in.xf[0], in.xf[1], in.xf[2], mk3(in.pos[i0 * 3], in.pos[i0 * 3 + 1], in.pos[i0 * 3 + 2]));
+            float3 p1 = ix_point(in.xf[0], in.xf[1], in.xf[2], mk3(in.pos[i1 * 3], in.pos[i1 * 3 + 1], in.pos[i1 * 3 + 2]));
+            float3 p2 = ix_point(in.xf[0], in.xf[1], in.xf[2], mk3(in.pos[i2 * 3], in.pos[i2 * 3 + 1], in.pos[i2 * 3 + 2]));
             lo = fmin3(p0, fmin3(p1, p2)), hi = fmax3(p0, fmax3(p1, p2));
-            float3 e1 = p1 - p0, e2 = p2 - p0;
+            float3 e1 = ix_sub(p1, p0), e2 = ix_sub(p2, p0);
             // the intersector reconstructs p1 = v0 + e1 in fp32; widen the box by that rounding
             lo = fmin3(lo, fmin3(p0 + e1, p0 + e2)), hi = fmax3(hi, fmax3(p0 + e1, p0 + e2));
             r.v0 = make_float4(p0.x, p0.y, p0.z, __uint_as_float(prim));

@@ -6,6 +6,8 @@
 //   * a compressed traversal stack of (node-group base, hit mask) pairs.
 // Intersection arithmetic (OptiX-internal in the reference) is fp32 Moeller-Trumbore on world-space
 // triangles and an analytic unit sphere in the instance's object space; a hit needs tmin < t < tmax.
+// It is spelled out with round-to-nearest intrinsics (ix_* below) so that nvcc cannot re-associate or
+// contract it: t, u, v depend only on this sequence, which a CPU checker can reproduce with fmaf().
 #pragma once
 #include "pb2_types.cuh"
 
@@ -26,35 +28,46 @@ struct TraceCounters {
 
 PB2_D uint32_t byte_of(uint32_t w, int i) { return (w >> (i * 8)) & 0xffu; }
 
+// fixed-rounding building blocks (the CPU checker used by the tests spells out the same sequence with fmaf)
+PB2_D float ix_dot(float3 a, float3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, __fmul_rn(a.x, b.x))); }
+PB2_D float3 ix_cross(float3 a, float3 b) {
+    return mk3(__fmaf_rn(a.y, b.z, -__fmul_rn(a.z, b.y)), __fmaf_rn(a.z, b.x, -__fmul_rn(a.x, b.z)), __fmaf_rn(a.x, b.y, -__fmul_rn(a.y, b.x)));
+}
+PB2_D float3 ix_sub(float3 a, float3 b) { return mk3(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y), __fsub_rn(a.z, b.z)); }
+PB2_D float ix_row_point(float4 r, float3 p) { return __fmaf_rn(r.z, p.z, __fmaf_rn(r.y, p.y, __fmaf_rn(r.x, p.x, r.w))); }
+PB2_D float ix_row_vector(float4 r, float3 v) { return __fmaf_rn(r.z, v.z, __fmaf_rn(r.y, v.y, __fmul_rn(r.x, v.x))); }
+PB2_D float3 ix_point(float4 r0, float4 r1, float4 r2, float3 p) { return mk3(ix_row_point(r0, p), ix_row_point(r1, p), ix_row_point(r2, p)); }
+PB2_D float3 ix_vector(float4 r0, float4 r1, float4 r2, float3 v) { return mk3(ix_row_vector(r0, v), ix_row_vector(r1, v), ix_row_vector(r2, v)); }
+
 // Tests one primitive record.  Returns true when it is hit closer than `hit.t`.
 PB2_D bool intersect_prim(const SceneView &sv, uint32_t slot, float3 o, float3 d, float tmin, RayHit &hit) {
     const float4 *rec = reinterpret_cast<const float4 *>(sv.prims + slot);
     const float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
     if (__float_as_uint(c.w) == 0u) {
         const float3 v0 = mk3(a), e1 = mk3(b), e2 = mk3(c);
-        const float3 pvec = cross(d, e2);
-        const float det = dot(e1, pvec);
+        const float3 pvec = ix_cross(d, e2);
+        const float det = ix_dot(e1, pvec);
         if (det == 0.f) return false;
-        const float inv = 1.f / det;
-        const float3 tvec = o - v0;
-        const float u = dot(tvec, pvec) * inv;
+        const float inv = __fdiv_rn(1.f, det);
+        const float3 tvec = ix_sub(o, v0);
+        const float u = __fmul_rn(ix_dot(tvec, pvec), inv);
         if (u < 0.f || u > 1.f) return false;
-        const float3 qvec = cross(tvec, e1);
-        const float v = dot(d, qvec) * inv;
-        if (v < 0.f || u + v > 1.f) return false;
-        const float t = dot(e2, qvec) * inv;
+        const float3 qvec = ix_cross(tvec, e1);
+        const float v = __fmul_rn(ix_dot(d, qvec), inv);
+        if (v < 0.f || __fadd_rn(u, v) > 1.f) return false;
+        const float t = __fmul_rn(ix_dot(e2, qvec), inv);
         if (!(t > tmin && t < hit.t)) return false;
         hit.t = t, hit.u = u, hit.v = v, hit.prim_slot = slot;
         return true;
     } else {
         const DevInstance *in = sv.instances + __float_as_uint(b.w);
         const float4 r0 = __ldg(&in->inv[0]), r1 = __ldg(&in->inv[1]), r2 = __ldg(&in->inv[2]);
-        const float3 oo = xf_point(r0, r1, r2, o), dd = xf_vector(r0, r1, r2, d);
-        const float qa = dot(dd, dd), qb = dot(oo, dd), qc = dot(oo, oo) - 1.f;
-        const float disc = qb * qb - qa * qc;
+        const float3 oo = ix_point(r0, r1, r2, o), dd = ix_vector(r0, r1, r2, d);
+        const float qa = ix_dot(dd, dd), qb = ix_dot(oo, dd), qc = __fadd_rn(ix_dot(oo, oo), -1.f);
+        const float disc = __fmaf_rn(qb, qb, -__fmul_rn(qa, qc));
         if (!(disc >= 0.f) || qa == 0.f) return false;
-        const float sq = sqrtf(disc);
-        const float t0 = (-qb - sq) / qa, t1 = (-qb + sq) / qa;
+        const float sq = __fsqrt_rn(disc);
+        const float t0 = __fdiv_rn(__fsub_rn(-qb, sq), qa), t1 = __fdiv_rn(__fadd_rn(-qb, sq), qa);
         float t;
         if (t0 > tmin && t0 < hit.t) t = t0;
         else if (t1 > tmin && t1 < hit.t) t = t1;

@@ -1,0 +1,212 @@
+// extern "C" veneer over the C++ host surface (include/pupil_host.h).  No logic of its own.
+#include "../../include/pupil_host.h"
+#include "pt_pass.h"
+
+#include <cstring>
+#include <memory>
+#include <string>
+
+using namespace Pupil;
+
+namespace {
+std::string g_error;
+std::unique_ptr<pt::PTPass> g_pass;
+int Fail(const std::string &m) {
+    g_error = m;
+    return 1;
+}
+world::World *W() { return util::Singleton<world::World>::instance(); }
+System *Sys() { return util::Singleton<System>::instance(); }
+bool Ready() { return Sys()->IsInitialized() && g_pass; }
+bool HasWorld() { return W()->scene && W()->camera && W()->emitters; }
+}// namespace
+
+extern "C" {
+const char *pupil_last_error(void) { return g_error.c_str(); }
+int pupil_set_log_level(int level) {
+    Log::level = level;
+    return 0;
+}
+int pupil_init(int device) {
+    if (Sys()->IsInitialized()) pupil_shutdown();
+    Sys()->device = device;
+    Sys()->Init(false);
+    if (!Sys()->IsInitialized()) return Fail(std::string("System::Init failed: ") + pb2_last_error());
+    g_pass = std::make_unique<pt::PTPass>("Path Tracing");
+    Sys()->AddPass(g_pass.get());
+    return 0;
+}
+int pupil_shutdown(void) {
+    if (g_pass) Sys()->RemovePass(g_pass.get());
+    g_pass.reset();
+    if (Sys()->IsInitialized()) Sys()->Destroy();
+    return 0;
+}
+int pupil_load_scene_xml(const char *path) {
+    if (!Ready()) return Fail("pupil_init first");
+    if (!path || !std::filesystem::exists(path)) return Fail(std::string("scene file does not exist: ") + (path ? path : "(null)"));
+    Sys()->SetScene(std::filesystem::path(path));
+    if (!g_pass->GetLaunchParams().accum_buffer) return Fail("scene load failed");
+    return 0;
+}
+int pupil_load_scene_xml_string(const char *xml, const char *root_dir) {
+    if (!Ready()) return Fail("pupil_init first");
+    if (!xml) return Fail("null xml");
+    if (!W()->scene->LoadFromXMLString(xml, root_dir ? std::filesystem::path(root_dir) : std::filesystem::path())) return Fail("XML parse failed");
+    Sys()->SetScene(W()->scene.get());
+    if (!g_pass->GetLaunchParams().accum_buffer) return Fail("scene load failed");
+    return 0;
+}
+int pupil_parse_scene_xml(const char *path) {
+    if (!HasWorld()) W()->Init();
+    if (!path || !std::filesystem::exists(path)) return Fail(std::string("scene file does not exist: ") + (path ? path : "(null)"));
+    if (!W()->scene->LoadFromXML(std::filesystem::path(path)) || !W()->LoadScene(W()->scene.get())) return Fail("scene load failed");
+    return 0;
+}
+int pupil_parse_scene_xml_string(const char *xml, const char *root_dir) {
+    if (!HasWorld()) W()->Init();
+    if (!xml) return Fail("null xml");
+    if (!W()->scene->LoadFromXMLString(xml, root_dir ? std::filesystem::path(root_dir) : std::filesystem::path()) || !W()->LoadScene(W()->scene.get()))
+        return Fail("XML parse failed");
+    return 0;
+}
+int pupil_register_mesh(const char *key, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t nv, uint32_t nf) {
+    if (!key || std::strncmp(key, "mem:", 4) != 0) return Fail("mesh keys must start with \"mem:\"");
+    if (!util::Singleton<resource::ShapeManager>::instance()->LoadMeshShape(key, pos, nrm, uv, idx, nv, nf)) return Fail("empty mesh");
+    return 0;
+}
+int pupil_clear_shapes(void) {
+    util::Singleton<resource::ShapeManager>::instance()->Clear();
+    return 0;
+}
+int pupil_pass_config(int max_depth, int accumulate, uint32_t frames_per_run, uint32_t first_seed, uint32_t seed_stride, int sum_mode) {
+    if (!Ready()) return Fail("pupil_init first");
+    if (max_depth > 0) g_pass->SetMaxDepth(max_depth);
+    g_pass->SetAccumulate(accumulate != 0);
+    g_pass->SetFramesPerRun(frames_per_run);
+    g_pass->SetSumMode(sum_mode != 0);
+    g_pass->Restart(first_seed, seed_stride);
+    return 0;
+}
+int pupil_run(uint64_t n) {
+    if (!Ready()) return Fail("pupil_init first");
+    if (!n) return 0;
+    Sys()->max_frames = n;
+    Sys()->Run();
+    return 0;
+}
+int pupil_pass_state(uint32_t *sample_cnt, uint32_t *random_seed) {
+    if (!Ready()) return Fail("pupil_init first");
+    if (sample_cnt) *sample_cnt = g_pass->GetLaunchParams().sample_cnt;
+    if (random_seed) *random_seed = g_pass->GetLaunchParams().random_seed;
+    return 0;
+}
+int pupil_buffer_info(const char *name, void **dptr, uint32_t *w, uint32_t *h, uint32_t *stride) {
+    Buffer *b = name ? util::Singleton<BufferManager>::instance()->GetBuffer(name) : nullptr;
+    if (!b) return Fail(std::string("no buffer named ") + (name ? name : "(null)"));
+    if (dptr) *dptr = b->cuda_ptr;
+    if (w) *w = b->desc.width;
+    if (h) *h = b->desc.height;
+    if (stride) *stride = b->desc.stride_in_byte;
+    return 0;
+}
+int pupil_buffer_download(const char *name, void *host, uint64_t bytes) {
+    Buffer *b = name ? util::Singleton<BufferManager>::instance()->GetBuffer(name) : nullptr;
+    if (!b) return Fail(std::string("no buffer named ") + (name ? name : "(null)"));
+    if (bytes > b->SizeInBytes()) return Fail("buffer is smaller than the request");
+    if (pb2_download(host, b->cuda_ptr, bytes) != PB2_OK) return Fail(pb2_last_error());
+    return 0;
+}
+int pupil_buffer_upload(const char *name, const void *host, uint64_t bytes) {
+    Buffer *b = name ? util::Singleton<BufferManager>::instance()->GetBuffer(name) : nullptr;
+    if (!b) return Fail(std::string("no buffer named ") + (name ? name : "(null)"));
+    if (bytes > b->SizeInBytes()) return Fail("buffer is smaller than the request");
+    if (pb2_upload(b->cuda_ptr, host, bytes) != PB2_OK) return Fail(pb2_last_error());
+    return 0;
+}
+int pupil_get_film(uint32_t *w, uint32_t *h, uint32_t *max_depth) {
+    if (!HasWorld()) return Fail("no scene");
+    if (w) *w = W()->scene->sensor.film.w;
+    if (h) *h = W()->scene->sensor.film.h;
+    if (max_depth) *max_depth = W()->scene->integrator.max_depth;
+    return 0;
+}
+int pupil_get_camera(float s2c[16], float c2w[16], float *fov_y) {
+    if (!HasWorld()) return Fail("no scene");
+    const util::Mat4 a = W()->camera->GetSampleToCameraMatrix(), b = W()->camera->GetToWorldMatrix();
+    if (s2c) std::memcpy(s2c, a.e, 64);
+    if (c2w) std::memcpy(c2w, b.e, 64);
+    if (fov_y) *fov_y = W()->camera->GetDesc().fov_y;
+    return 0;
+}
+int pupil_num_instances(void) { return HasWorld() ? (int)W()->GetRenderobjects().size() : 0; }
+int pupil_get_instance(uint32_t index, float xform[16], pb2_material *material, int32_t *emitter_offset, uint32_t *flags, uint32_t *n_prims,
+                       int32_t *is_sphere) {
+    if (!HasWorld()) return Fail("no scene");
+    auto ros = W()->GetRenderobjects();
+    if (index >= ros.size()) return Fail("instance index out of range");
+    int offset = 0, mine = -1;
+    for (uint32_t i = 0; i <= index; ++i)
+        if (ros[i]->is_emitter) {
+            if (i == index) mine = offset;
+            offset += (int)ros[i]->sub_emitters_num;
+        }
+    const world::RenderObject *ro = ros[index];
+    if (xform) std::memcpy(xform, ro->transform.matrix.e, 64);
+    if (material) *material = ro->mat;
+    if (emitter_offset) *emitter_offset = mine;
+    if (flags) *flags = (ro->flip_normals ? PB2_INST_FLIP_NORMALS : 0u) | (ro->flip_tex_coords ? PB2_INST_FLIP_TEX : 0u);
+    if (n_prims) *n_prims = ro->sub_emitters_num;
+    if (is_sphere) *is_sphere = ro->geo_type == world::RenderObject::EGeoType::Sphere;
+    return 0;
+}
+int pupil_num_area_emitters(void) { return HasWorld() ? (int)W()->emitters->GetAreaEmitters().size() : 0; }
+int pupil_get_emitters(pb2_emitter *areas, pb2_emitter *env, int32_t *has_env) {
+    if (!HasWorld()) return Fail("no scene");
+    auto &a = W()->emitters->GetAreaEmitters();
+    if (areas && !a.empty()) std::memcpy(areas, a.data(), a.size() * sizeof(pb2_emitter));
+    const pb2_emitter *e = W()->emitters->GetEnvEmitter();
+    if (has_env) *has_env = e != nullptr;
+    if (env && e) *env = *e;
+    return 0;
+}
+int pupil_scene_handle(pb2_scene **scene) {
+    if (!Ready() || !scene) return Fail("no scene");
+    *scene = W()->GetSceneHandle();
+    return *scene ? 0 : Fail("no device scene");
+}
+int pupil_set_bvh_builder(int builder) {
+    if (!Ready()) return Fail("pupil_init first");
+    W()->SetBvhBuilder(builder);
+    return 0;
+}
+int pupil_build_stats(pb2_build_stats *stats) {
+    if (!Ready() || !stats) return Fail("no scene");
+    W()->GetSceneHandle();
+    *stats = W()->GetBuildStats();
+    return 0;
+}
+int pupil_render_stats(pb2_render_stats *stats) {
+    if (!Ready() || !stats) return Fail("no scene");
+    *stats = g_pass->GetRenderStats();
+    return 0;
+}
+int pupil_camera_move(float dx, float dy, float dz) {
+    if (!Ready() || !W()->camera) return Fail("no scene");
+    W()->camera->Move(util::Float3{ dx, dy, dz });
+    EventDispatcher<EWorldEvent::CameraChange>();
+    return 0;
+}
+int pupil_camera_rotate(float delta_x, float delta_y) {
+    if (!Ready() || !W()->camera) return Fail("no scene");
+    W()->camera->Rotate(delta_x, delta_y);
+    EventDispatcher<EWorldEvent::CameraChange>();
+    return 0;
+}
+int pupil_camera_set_fov(float fov_y) {
+    if (!Ready() || !W()->camera) return Fail("no scene");
+    W()->camera->SetFov(fov_y);
+    EventDispatcher<EWorldEvent::CameraChange>();
+    return 0;
+}
+}

@@ -1,0 +1,93 @@
+// path_tracer — headless counterpart of example/path_tracer/main.cpp:5-22:
+//   System::Init -> AddPass(PTPass) -> SetScene(xml) -> Run -> Destroy
+// plus what a window-less run needs: an spp limit and an image file.
+//   path_tracer --scene file.xml [--spp 64] [--depth N] [--device 0] [--out image.pfm] [--batch 16] [--builder 0|1]
+#include "pt_pass.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <memory>
+#include <vector>
+
+using namespace Pupil;
+
+// Portable FloatMap, RGB, little endian.  PFM stores the BOTTOM row first — the buffers' native order (row 0 =
+// bottom, as in the reference's screenshot path util/texture.cpp:37).
+static bool WritePfm(const char *path, const std::vector<float> &rgba, uint32_t w, uint32_t h) {
+    std::ofstream f(path, std::ios::binary);
+    if (!f) return false;
+    f << "PF\n" << w << " " << h << "\n-1.0\n";
+    std::vector<float> row(w * 3);
+    for (uint32_t y = 0; y < h; ++y) {
+        for (uint32_t x = 0; x < w; ++x)
+            for (int c = 0; c < 3; ++c) row[x * 3 + c] = rgba[(static_cast<size_t>(y) * w + x) * 4 + c];
+        f.write(reinterpret_cast<const char *>(row.data()), row.size() * sizeof(float));
+    }
+    return static_cast<bool>(f);
+}
+
+int main(int argc, char **argv) {
+    const char *scene_path = nullptr, *out_path = "path_tracer.pfm";
+    unsigned spp = 64, batch = 16;
+    int depth = 0, device = 0, builder = -1;
+    for (int i = 1; i < argc; ++i) {
+        auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+        if (!std::strcmp(argv[i], "--scene")) scene_path = next();
+        else if (!std::strcmp(argv[i], "--spp")) spp = std::max(1, std::atoi(next()));
+        else if (!std::strcmp(argv[i], "--depth")) depth = std::atoi(next());
+        else if (!std::strcmp(argv[i], "--device")) device = std::atoi(next());
+        else if (!std::strcmp(argv[i], "--out")) out_path = next();
+        else if (!std::strcmp(argv[i], "--batch")) batch = std::max(1, std::atoi(next()));
+        else if (!std::strcmp(argv[i], "--builder")) builder = std::atoi(next());
+        else if (!std::strcmp(argv[i], "--verbose")) Log::level = 2;
+        else {
+            std::fprintf(stderr, "usage: %s --scene file.xml [--spp N] [--depth N] [--device D] [--out image.pfm] [--batch N] [--builder 0|1]\n", argv[0]);
+            return 2;
+        }
+    }
+    if (!scene_path) {
+        std::fprintf(stderr, "path_tracer: --scene is required\n");
+        return 2;
+    }
+    auto *system = util::Singleton<System>::instance();
+    system->device = device;
+    system->Init(false);
+    if (!system->IsInitialized()) return 1; // no CUDA device: there is no CPU path
+    int rc = 0;
+    {
+        auto pt_pass = std::make_unique<pt::PTPass>("Path Tracing");
+        system->AddPass(pt_pass.get());
+        if (builder >= 0) util::Singleton<world::World>::instance()->SetBvhBuilder(builder);
+        system->SetScene(std::filesystem::path(scene_path));
+        if (!pt_pass->GetLaunchParams().accum_buffer) {
+            std::fprintf(stderr, "path_tracer: could not load %s\n", scene_path);
+            rc = 1;
+        } else {
+            if (depth > 0) pt_pass->SetMaxDepth(depth);
+            Timer timer;
+            timer.Start();
+            unsigned done = 0;
+            while (done < spp) { // whole batches, then the remainder
+                const unsigned n = std::min(batch, spp - done);
+                pt_pass->SetFramesPerRun(n);
+                system->max_frames = 1;
+                system->Run();
+                done += n;
+            }
+            timer.Stop();
+            const auto &lp = pt_pass->GetLaunchParams();
+            const uint32_t w = lp.config.frame.width, h = lp.config.frame.height;
+            std::vector<float> img(static_cast<size_t>(w) * h * 4);
+            pb2_download(img.data(), lp.frame_buffer, img.size() * sizeof(float));
+            const auto &bs = util::Singleton<world::World>::instance()->GetBuildStats();
+            std::printf("%ux%u, %u spp, depth %u: %.1f ms (%.2f Msamples/s); BVH: %llu prims, %llu nodes, %.2f ms\n", w, h, spp, lp.config.max_depth,
+                        timer.ElapsedMilliseconds(), 1e-3 * w * h * spp / timer.ElapsedMilliseconds(), (unsigned long long)bs.n_prims,
+                        (unsigned long long)bs.n_nodes, bs.build_ms);
+            if (!WritePfm(out_path, img, w, h)) std::fprintf(stderr, "path_tracer: cannot write %s\n", out_path), rc = 1;
+        }
+        system->RemovePass(pt_pass.get());
+    }
+    system->Destroy();
+    return rc;
+}

@@ -1,0 +1,57 @@
+// Pupil::pt::PTPass — the path-tracing pass of example/path_tracer (pt_pass.{h,cpp}, type.h), same class and
+// buffer names, with optix::Pass::Run + Synchronize replaced by pb2_render + pb2_synchronize.
+//
+// One OnRun() is one frame = one sample per pixel, exactly as in the reference (pt_pass.cpp:39-57); the
+// progressive state is (accum buffer, sample_cnt, random_seed), reset whenever the pass is dirty.
+// SetFramesPerRun(n) lets one OnRun() execute n consecutive frames inside the back end (same seeds, same
+// running mean, no host round trip in between) — n = 1 is the reference behaviour.
+#pragma once
+#include "system.h"
+
+#include <atomic>
+
+namespace Pupil::pt {
+// pt::OptixLaunchParams (type.h:9-33): camera, emitter group and the AS handle live in the pb2 scene
+struct LaunchParams {
+    struct {
+        unsigned int max_depth = 1;
+        bool accumulated_flag = true;
+        struct {
+            unsigned int width = 0, height = 0;
+        } frame;
+    } config;
+    unsigned int random_seed = 0;
+    unsigned int sample_cnt = 0;
+    void *accum_buffer = nullptr, *frame_buffer = nullptr, *normal_buffer = nullptr, *albedo_buffer = nullptr, *test = nullptr;
+    pb2_scene *handle = nullptr;
+};
+
+class PTPass : public Pass {
+public:
+    PTPass(std::string_view name = "Path Tracing") noexcept;
+    ~PTPass() noexcept override;
+    void OnRun() noexcept override;
+    void Inspector() noexcept override;
+    void SetScene(world::World *world) noexcept;
+
+    // the two inspector knobs of the reference (pt_pass.cpp:256-268)
+    void SetMaxDepth(int max_depth) noexcept;
+    void SetAccumulate(bool accumulate) noexcept;
+    void SetFramesPerRun(unsigned int n) noexcept { m_frames_per_run = n ? n : 1; }
+    // restart the progressive sequence at a given seed without touching the scene (checkpoint / shard support)
+    void Restart(unsigned int first_seed = 0, unsigned int seed_stride = 1) noexcept;
+    void SetSumMode(bool sum) noexcept { m_sum_mode = sum, m_dirty = true; } // accumulate plain sums (multi-GPU shards)
+    const LaunchParams &GetLaunchParams() const noexcept { return m_params; }
+    pb2_render_stats GetRenderStats() noexcept;
+
+private:
+    void BindingEventCallback() noexcept;
+    LaunchParams m_params;
+    size_t m_output_pixel_num = 0;
+    std::atomic_bool m_dirty = true;
+    world::World *m_world = nullptr;
+    int m_max_depth = 1;
+    bool m_accumulated_flag = true, m_sum_mode = false;
+    unsigned int m_frames_per_run = 1, m_first_seed = 0, m_seed_stride = 1;
+};
+}// namespace Pupil::pt

@@ -1,0 +1,214 @@
+"""ctypes binding of libpupil_host.so (include/pupil_host.h): the reference's host surface —
+System::Init / AddPass(PTPass) / SetScene / Run, World, BufferManager — re-implemented in C++ under
+pupiloptixlab_b200/host/ on top of the pb2 CUDA back end.
+
+    from pupiloptixlab_b200 import pupil, scenes
+    pupil.init(0)
+    pupil.load_scene(scenes.cornell_box(512, 512, 8))       # or pupil.load_scene_xml("cornellbox.xml")
+    pupil.run(64)                                            # 64 x PTPass::OnRun = 64 spp
+    img = pupil.buffer("final result")                       # (H, W, 4) float32, row 0 = bottom
+
+No CPU path exists: without the built libraries or without a CUDA device, init() raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import pb2
+from .scenes import SceneDesc, to_xml_string
+
+LIB_PATH = pb2.PKG / "_build" / "libpupil_host.so"
+u32, i32, f32, u64 = C.c_uint32, C.c_int32, C.c_float, C.c_uint64
+_lib = None
+_mesh_serial = 0
+_keepalive = []
+
+
+class PupilError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        pb2.lib()  # libpb2.so first (also resolved through the rpath)
+        if not LIB_PATH.exists():
+            raise PupilError(f"{LIB_PATH} not found: run `python -m pupiloptixlab_b200.build`")
+        L = C.CDLL(str(LIB_PATH))
+        P, vp = C.POINTER, C.c_void_p
+        L.pupil_last_error.restype = C.c_char_p
+        sigs = {
+            "pupil_init": [C.c_int], "pupil_shutdown": [], "pupil_set_log_level": [C.c_int], "pupil_load_scene_xml": [C.c_char_p],
+            "pupil_load_scene_xml_string": [C.c_char_p, C.c_char_p],
+            "pupil_parse_scene_xml": [C.c_char_p], "pupil_parse_scene_xml_string": [C.c_char_p, C.c_char_p], "pupil_register_mesh": [C.c_char_p, vp, vp, vp, vp, u32, u32],
+            "pupil_clear_shapes": [], "pupil_pass_config": [C.c_int, C.c_int, u32, u32, u32, C.c_int], "pupil_run": [u64],
+            "pupil_pass_state": [P(u32), P(u32)], "pupil_buffer_info": [C.c_char_p, P(vp), P(u32), P(u32), P(u32)],
+            "pupil_buffer_download": [C.c_char_p, vp, u64], "pupil_buffer_upload": [C.c_char_p, vp, u64],
+            "pupil_get_film": [P(u32), P(u32), P(u32)], "pupil_get_camera": [P(f32), P(f32), P(f32)], "pupil_num_instances": [],
+            "pupil_get_instance": [u32, P(f32), P(pb2.Material), P(i32), P(u32), P(u32), P(i32)], "pupil_num_area_emitters": [],
+            "pupil_get_emitters": [P(pb2.Emitter), P(pb2.Emitter), P(i32)], "pupil_scene_handle": [P(vp)], "pupil_set_bvh_builder": [C.c_int],
+            "pupil_build_stats": [P(pb2.BuildStats)], "pupil_render_stats": [P(pb2.RenderStats)], "pupil_camera_move": [f32, f32, f32],
+            "pupil_camera_rotate": [f32, f32], "pupil_camera_set_fov": [f32],
+        }
+        for name, args in sigs.items():
+            fn = getattr(L, name)
+            fn.argtypes, fn.restype = args, C.c_int
+        _lib = L
+    return _lib
+
+
+def check(code: int):
+    if code != 0:
+        raise PupilError(lib().pupil_last_error().decode())
+
+
+def init(device: int = 0, log_level: int = 1):
+    L = lib()
+    if pb2.lib().pb2_device_count() <= 0:
+        raise PupilError("no CUDA device visible: there is no CPU fallback")
+    L.pupil_set_log_level(log_level)
+    check(L.pupil_init(device))
+
+
+def shutdown():
+    lib().pupil_shutdown()
+    lib().pupil_clear_shapes()
+    _keepalive.clear()
+
+
+def load_scene_xml(path):
+    check(lib().pupil_load_scene_xml(str(path).encode()))
+
+
+def parse_scene_xml(path):
+    """Host-only: parse + World precompute without a device (inspection through camera() / instances() / emitters())."""
+    check(lib().pupil_parse_scene_xml(str(path).encode()))
+
+
+def load_scene(desc: SceneDesc, host_only: bool = False):
+    """SceneDesc -> XML text (in memory) -> the host library's loader; triangle meshes go across as arrays."""
+    global _mesh_serial
+    names = {}
+    for i, sh in enumerate(desc.shapes):
+        if sh.type != "obj":
+            continue
+        _mesh_serial += 1
+        key = f"mem:{desc.name}_{i}_{_mesh_serial}"
+        m = sh.mesh
+        P = np.ascontiguousarray(m["positions"], np.float32).reshape(-1, 3)
+        I = np.ascontiguousarray(m["indices"], np.uint32).reshape(-1, 3)
+        N = None if m.get("normals") is None else np.ascontiguousarray(m["normals"], np.float32)
+        T = None if m.get("texcoords") is None else np.ascontiguousarray(m["texcoords"], np.float32)
+        check(lib().pupil_register_mesh(key.encode(), pb2._ptr(P), pb2._ptr(N), pb2._ptr(T), pb2._ptr(I), P.shape[0], I.shape[0]))
+        names[i] = key
+    fn = lib().pupil_parse_scene_xml_string if host_only else lib().pupil_load_scene_xml_string
+    check(fn(to_xml_string(desc, names).encode(), None))
+
+
+def pass_config(max_depth: int = 0, accumulate: bool = True, frames_per_run: int = 1, first_seed: int = 0, seed_stride: int = 1,
+                sum_mode: bool = False):
+    check(lib().pupil_pass_config(max_depth, int(accumulate), frames_per_run, first_seed, seed_stride, int(sum_mode)))
+
+
+def run(n_pass_runs: int = 1):
+    check(lib().pupil_run(n_pass_runs))
+
+
+def pass_state():
+    a, b = u32(), u32()
+    check(lib().pupil_pass_state(C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def buffer_info(name: str):
+    p, w, h, s = C.c_void_p(), u32(), u32(), u32()
+    check(lib().pupil_buffer_info(name.encode(), C.byref(p), C.byref(w), C.byref(h), C.byref(s)))
+    return p.value, w.value, h.value, s.value
+
+
+def buffer(name: str) -> np.ndarray:
+    """Download a named buffer as (H, W, C) float32 (row 0 = bottom of the image)."""
+    _, w, h, stride = buffer_info(name)
+    out = np.empty((h, w, stride // 4), np.float32)
+    check(lib().pupil_buffer_download(name.encode(), pb2._ptr(out), out.nbytes))
+    return out
+
+
+def film():
+    w, h, d = u32(), u32(), u32()
+    check(lib().pupil_get_film(C.byref(w), C.byref(h), C.byref(d)))
+    return w.value, h.value, d.value
+
+
+def camera():
+    a, b, fov = np.zeros(16, np.float32), np.zeros(16, np.float32), f32()
+    check(lib().pupil_get_camera(a.ctypes.data_as(C.POINTER(f32)), b.ctypes.data_as(C.POINTER(f32)), C.byref(fov)))
+    return a.reshape(4, 4), b.reshape(4, 4), fov.value
+
+
+def instances():
+    out = []
+    for i in range(lib().pupil_num_instances()):
+        xf, mat = np.zeros(16, np.float32), pb2.Material()
+        eo, fl, npr, sph = i32(), u32(), u32(), i32()
+        check(lib().pupil_get_instance(i, xf.ctypes.data_as(C.POINTER(f32)), C.byref(mat), C.byref(eo), C.byref(fl), C.byref(npr), C.byref(sph)))
+        out.append(dict(xform=xf.reshape(4, 4), material=mat, emitter_offset=eo.value, flags=fl.value, n_prims=npr.value, is_sphere=bool(sph.value)))
+    return out
+
+
+def emitters():
+    n = lib().pupil_num_area_emitters()
+    arr = (pb2.Emitter * max(1, n))()
+    env, has = pb2.Emitter(), i32()
+    check(lib().pupil_get_emitters(arr, C.byref(env), C.byref(has)))
+    return list(arr)[:n], (env if has.value else None)
+
+
+class _BorrowedScene(pb2.Scene):
+    """pb2.Scene view of the World's device scene (not owned: never destroyed from Python)."""
+
+    def __init__(self, handle):  # noqa: super().__init__ would create a new scene
+        self.h = C.c_void_p(handle)
+
+    def close(self):
+        self.h = C.c_void_p()
+
+    def __del__(self):
+        pass
+
+
+def scene_handle() -> pb2.Scene:
+    h = C.c_void_p()
+    check(lib().pupil_scene_handle(C.byref(h)))
+    return _BorrowedScene(h.value)
+
+
+def set_bvh_builder(builder: int):
+    check(lib().pupil_set_bvh_builder(builder))
+
+
+def build_stats() -> pb2.BuildStats:
+    st = pb2.BuildStats()
+    check(lib().pupil_build_stats(C.byref(st)))
+    return st
+
+
+def render_stats() -> pb2.RenderStats:
+    st = pb2.RenderStats()
+    check(lib().pupil_render_stats(C.byref(st)))
+    return st
+
+
+def camera_move(dx, dy, dz):
+    check(lib().pupil_camera_move(dx, dy, dz))
+
+
+def camera_rotate(dx, dy):
+    check(lib().pupil_camera_rotate(dx, dy))
+
+
+def camera_set_fov(fov_y):
+    check(lib().pupil_camera_set_fov(fov_y))

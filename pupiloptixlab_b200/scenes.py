@@ -299,10 +299,9 @@ def write_obj(path: Path, mesh: dict) -> None:
                 f.write(f"f {a} {b} {c}\n")
 
 
-def to_xml(scene: SceneDesc, path) -> Path:
-    """Write `scene` as a mitsuba3-style XML the reference's loader dialect accepts; obj meshes are
-    written next to it."""
-    path = Path(path)
+def to_xml_string(scene: SceneDesc, obj_names: dict) -> str:
+    """`scene` in the mitsuba3-style dialect the reference's loader accepts.  obj_names maps shape index ->
+    the file name (or "mem:KEY") written for that obj shape."""
     s = '<scene version="3.0.0">\n'
     s += f'\t<default name="max_depth" value="{int(scene.max_depth)}" />\n'
     s += f'\t<default name="resx" value="{int(scene.sensor.width)}" />\n\t<default name="resy" value="{int(scene.sensor.height)}" />\n'
@@ -317,9 +316,7 @@ def to_xml(scene: SceneDesc, path) -> Path:
     for i, sh in enumerate(scene.shapes):
         s += f'\t<shape type="{sh.type}" id="{sh.name or f"shape{i}"}">\n'
         if sh.type == "obj":
-            obj_name = f"{path.stem}_{i}.obj"
-            write_obj(path.parent / obj_name, sh.mesh)
-            s += f'\t\t<string name="filename" value="{obj_name}" />\n'
+            s += f'\t\t<string name="filename" value="{obj_names[i]}" />\n'
             s += f'\t\t<boolean name="flip_tex_coords" value="{"true" if sh.flip_tex_coords else "false"}" />\n'
         if sh.type == "sphere":
             s += f'\t\t<point name="center" x="{_f(sh.center[0])}" y="{_f(sh.center[1])}" z="{_f(sh.center[2])}" />\n'
@@ -334,5 +331,16 @@ def to_xml(scene: SceneDesc, path) -> Path:
     if scene.env_radiance is not None:
         s += f'\t<emitter type="constant">\n\t\t<rgb name="radiance" value="{_csv(scene.env_radiance)}" />\n\t</emitter>\n'
     s += "</scene>\n"
-    path.write_text(s)
+    return s
+
+
+def to_xml(scene: SceneDesc, path) -> Path:
+    """Write `scene` as an XML file; obj meshes are written next to it as Wavefront .obj files."""
+    path = Path(path)
+    names = {}
+    for i, sh in enumerate(scene.shapes):
+        if sh.type == "obj":
+            names[i] = f"{path.stem}_{i}.obj"
+            write_obj(path.parent / names[i], sh.mesh)
+    path.write_text(to_xml_string(scene, names))
     return path

@@ -37,7 +37,8 @@ def test_closest_hit_matches_brute_force(port_lib, n_tris, n_spheres, builder):
     gpu = s.trace_closest(rays)
     ties = compare_hits(gpu, ref, rays)
     assert ties <= len(rays) // 200
-    assert np.count_nonzero(ref["inst"] >= 0) > len(rays) // 20  # the batch actually hits things
+    if n_tris >= 1000:
+        assert np.count_nonzero(ref["inst"] >= 0) > len(rays) // 20  # the batch actually hits things
     # barycentrics agree where ids agree
     m = (gpu["inst"] == ref["inst"]) & (gpu["prim"] == ref["prim"]) & (ref["inst"] >= 0)
     assert np.allclose(gpu["u"][m], ref["u"][m], atol=2e-4) and np.allclose(gpu["v"][m], ref["v"][m], atol=2e-4)
