@@ -111,7 +111,11 @@ typedef struct pb2_render_stats {
     uint64_t kernel_launches;           /* kernels launched by the last pb2_render call */
     float total_ms;                     /* device time of the last pb2_render call (CUDA events on the scene's stream) */
     float generate_ms, extend_ms, shade_ms, shadow_ms, accumulate_ms; /* per stage, only when profiling is on */
-    uint64_t nodes_visited, prims_tested;                             /* traversal counters, only when counting is on */
+    uint64_t nodes_visited, prims_tested;                             /* traversal counters (closest + shadow), only when counting is on */
+    uint64_t nodes_shadow, prims_shadow;                              /* the shadow-ray share of the two counters above */
+    uint32_t batches, rounds;                                         /* wavefront batches executed, bounce rounds per batch */
+    uint32_t extend_launches, shade_launches, shadow_launches, other_launches; /* kernel launches by stage */
+    uint64_t shaded_paths;                                            /* path-vertex shading invocations (= closest rays traced) */
 } pb2_render_stats;
 
 /* ---- library / device ------------------------------------------------------------------------------- */

@@ -44,7 +44,7 @@ struct Wavefront {
     std::vector<Ev> events;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     uint64_t launches = 0;
-    uint32_t rounds_used = 0, batches = 0;
+    uint32_t rounds_used = 0, batches = 0, n_extend = 0, n_shade = 0, n_shadow = 0;
     bool stats_pending = false;
 
     void ensure(uint64_t paths, uint32_t rounds) {
@@ -481,7 +481,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
 
     for (auto &e : wf.events) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
     wf.events.clear();
-    wf.launches = 0, wf.batches = 0, wf.rounds_used = rounds;
+    wf.launches = 0, wf.batches = 0, wf.rounds_used = rounds, wf.n_extend = wf.n_shade = wf.n_shadow = 0;
     auto stage_begin = [&](int stage) {
         if (!s.profiling) return;
         Wavefront::Ev e{ stage, nullptr, nullptr };
@@ -533,14 +533,14 @@ void render(Scene &s, const pb2_launch_params &lp) {
             k_shade<<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
             PB2_LAUNCH_CHECK();
             stage_end();
-            wf.launches += 2;
+            wf.launches += 2, ++wf.n_extend, ++wf.n_shade;
             if (r + 1 < rounds) { // the last round cannot emit rays (depth >= max_depth)
                 stage_begin(3);
                 if (s.counting) k_shadow<true><<<grid_trace, 128, 0, st>>>(sv, pa, wf.q_shadow.ptr, ctr + CTR_SHADOW, wf.trav_counters.ptr);
                 else k_shadow<false><<<grid_trace, 128, 0, st>>>(sv, pa, wf.q_shadow.ptr, ctr + CTR_SHADOW, nullptr);
                 PB2_LAUNCH_CHECK();
                 stage_end();
-                ++wf.launches;
+                ++wf.launches, ++wf.n_shadow;
             }
         }
         stage_begin(4);
@@ -552,6 +552,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
         if (lp.accumulate == 1) sample_cnt += frames;
         k_collect_counts<<<1, 32, 0, st>>>(wf.counters.ptr, rounds, wf.ray_totals.ptr);
         PB2_LAUNCH_CHECK();
+        ++wf.launches;
         ++wf.batches;
     }
     PB2_CUDA(cudaEventRecord(wf.t1, st));
@@ -577,7 +578,12 @@ void collect_render_stats(Scene &s) {
         unsigned long long h[4];
         PB2_CUDA(cudaMemcpy(h, wf.trav_counters.ptr, sizeof h, cudaMemcpyDeviceToHost));
         rs.nodes_visited = h[0] + h[2], rs.prims_tested = h[1] + h[3];
+        rs.nodes_shadow = h[2], rs.prims_shadow = h[3];
     }
+    rs.batches = wf.batches, rs.rounds = wf.rounds_used;
+    rs.extend_launches = wf.n_extend, rs.shade_launches = wf.n_shade, rs.shadow_launches = wf.n_shadow;
+    rs.other_launches = (uint32_t)(wf.launches - wf.n_extend - wf.n_shade - wf.n_shadow);
+    rs.shaded_paths = rs.closest_rays;
     s.render_stats = rs;
     wf.stats_pending = false;
 }
