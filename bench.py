@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=2, help="spp of the CPU sample per step / for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="pb2 scene option name=value (tuning experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -221,6 +222,9 @@ def main():
     scene = pupil.scene_handle()
     scene.set_stream(stream.cuda_stream)
     scene.set_option("profiling", 1)  # per-stage CUDA events (a few dozen event records per batch)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        scene.set_option(k, int(v))
     build = pupil.build_stats()
     accum_ptr, _, _, _ = pupil.buffer_info("pt accum buffer")
     frame_ptr, _, _, _ = pupil.buffer_info("final result")

@@ -365,6 +365,8 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     if (n == "profiling") s.profiling = value != 0;
     else if (n == "counting") s.counting = value != 0;
     else if (n == "sort_by_material") s.sort_by_material = value != 0;
+    else if (n == "refill_threshold") s.refill_threshold = (int)std::min<int64_t>(33, std::max<int64_t>(0, value));
+    else if (n == "shade_variant") s.shade_variant = (int)value;
     else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);
     else return fail(PB2_ERR_ARG, "pb2_scene_set_option: unknown option " + n);
     return PB2_OK;

@@ -33,6 +33,7 @@ struct Scene {
 
     DevBuf<Bvh8Node> d_nodes;
     DevBuf<PrimRec> d_prims;
+    DevBuf<uint32_t> trace_work; // work counter of the persistent trace kernels
     uint32_t n_nodes = 0, n_prims = 0;
     bool bvh_valid = false;
     int builder = 1; // 0 LBVH, 1 binned SAH
@@ -41,7 +42,8 @@ struct Scene {
     // options
     bool profiling = false, counting = false, sort_by_material = true;
     uint64_t paths_in_flight = 0;
-    int trace_block = 0; // 0 = default
+    int refill_threshold = 26;
+    int shade_variant = 6;     // k_shade<MINB>: 4, 6 or 8 resident CTAs per SM // persistent traversal: refill idle lanes when fewer than this many are busy
 
     Wavefront *wf = nullptr;
     pb2_render_stats render_stats{};

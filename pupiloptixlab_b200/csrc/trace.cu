@@ -5,42 +5,61 @@
 
 namespace pb2 {
 namespace {
-template<bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_closest(SceneView sv, const float4 *__restrict__ rays, uint64_t n, float4 *__restrict__ hit_tuvp,
-                                                       int32_t *__restrict__ hit_inst, unsigned long long *__restrict__ counters) {
-    TraceCounters ctr{ 0, 0 };
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
-        RayHit h;
-        h.t = rd.w, h.u = h.v = 0.f;
-        traverse<false, COUNT>(sv, mk3(ro), mk3(rd), ro.w, h, &ctr);
+struct ClosestIO {
+    const float4 *__restrict__ rays;
+    float4 *__restrict__ hit_tuvp;
+    int32_t *__restrict__ hit_inst;
+    const PrimRec *prims;
+    uint32_t n;
+    PB2_D uint32_t size() const { return n; }
+    PB2_D uint32_t load(uint32_t i, float3 &o, float3 &d, float &tmin, float &tmax) const {
+        const float4 ro = __ldg(rays + 2 * (size_t)i), rd = __ldg(rays + 2 * (size_t)i + 1);
+        o = mk3(ro), d = mk3(rd), tmin = ro.w, tmax = rd.w;
+        return i;
+    }
+    PB2_D void commit(bool valid, uint32_t i, const RayHit &h, bool hit) const {
+        if (!valid) return;
         int32_t inst = -1;
         uint32_t prim = 0xffffffffu;
-        if (h.prim_slot != 0xffffffffu) {
-            const float4 *rec = reinterpret_cast<const float4 *>(sv.prims + h.prim_slot);
+        float t = 0.f;
+        if (hit) {
+            const float4 *rec = reinterpret_cast<const float4 *>(prims + h.prim_slot);
             prim = __float_as_uint(__ldg(rec).w);
             inst = (int32_t)__float_as_uint(__ldg(rec + 1).w);
-        } else {
-            h.t = 0.f;
+            t = h.t;
         }
-        hit_tuvp[i] = make_float4(h.t, h.u, h.v, __uint_as_float(prim));
+        hit_tuvp[i] = make_float4(t, h.u, h.v, __uint_as_float(prim));
         hit_inst[i] = inst;
     }
+};
+struct AnyIO {
+    const float4 *__restrict__ rays;
+    uint32_t *__restrict__ occluded;
+    uint32_t n;
+    PB2_D uint32_t size() const { return n; }
+    PB2_D uint32_t load(uint32_t i, float3 &o, float3 &d, float &tmin, float &tmax) const {
+        const float4 ro = __ldg(rays + 2 * (size_t)i), rd = __ldg(rays + 2 * (size_t)i + 1);
+        o = mk3(ro), d = mk3(rd), tmin = ro.w, tmax = rd.w;
+        return i;
+    }
+    PB2_D void commit(bool valid, uint32_t i, const RayHit &, bool hit) const {
+        if (valid) occluded[i] = hit ? 1u : 0u;
+    }
+};
+
+template<bool COUNT>
+__global__ void __launch_bounds__(128) k_trace_closest(SceneView sv, ClosestIO io, uint32_t *__restrict__ work, unsigned long long *__restrict__ counters, int thr) {
+    TraceCounters ctr{ 0, 0 };
+    trace_persistent<false, COUNT>(sv, io, work, &ctr, thr);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)ctr.nodes);
         atomicAdd(&counters[1], (unsigned long long)ctr.prims);
     }
 }
 template<bool COUNT>
-__global__ void __launch_bounds__(128) k_trace_any(SceneView sv, const float4 *__restrict__ rays, uint64_t n, uint32_t *__restrict__ occluded,
-                                                   unsigned long long *__restrict__ counters) {
+__global__ void __launch_bounds__(128) k_trace_any(SceneView sv, AnyIO io, uint32_t *__restrict__ work, unsigned long long *__restrict__ counters, int thr) {
     TraceCounters ctr{ 0, 0 };
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
-        RayHit h;
-        h.t = rd.w, h.u = h.v = 0.f;
-        occluded[i] = traverse<true, COUNT>(sv, mk3(ro), mk3(rd), ro.w, h, &ctr) ? 1u : 0u;
-    }
+    trace_persistent<true, COUNT>(sv, io, work, &ctr, thr);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)ctr.nodes);
         atomicAdd(&counters[1], (unsigned long long)ctr.prims);
@@ -56,40 +75,37 @@ unsigned trace_grid(uint64_t n, int block) {
 }
 }// namespace
 
-void trace_closest_dev(Scene &s, const float4 *rays, uint64_t n, float4 *hit_tuvp, int32_t *hit_inst) {
-    if (!s.bvh_valid) throw std::runtime_error("pb2_trace_closest: call pb2_bvh_build first");
-    if (!n) return;
+template<class K, class IO>
+void launch_trace(Scene &s, K kernel_plain, K kernel_count, const IO &io, uint64_t n) {
+    if (n >= 0xffffffffull) throw std::runtime_error("pb2_trace: more than 2^32-1 rays in one call");
     const SceneView sv = s.view();
+    s.trace_work.ensure(1);
+    PB2_CUDA(cudaMemsetAsync(s.trace_work.ptr, 0, sizeof(uint32_t), s.stream));
     if (s.counting) {
         DevBuf<unsigned long long> ctr(2);
         ctr.zero(s.stream);
-        k_trace_closest<true><<<trace_grid(n, 128), 128, 0, s.stream>>>(sv, rays, n, hit_tuvp, hit_inst, ctr.ptr);
+        kernel_count<<<trace_grid(n, 128), 128, 0, s.stream>>>(sv, io, s.trace_work.ptr, ctr.ptr, s.refill_threshold);
         PB2_LAUNCH_CHECK();
         unsigned long long h[2];
         PB2_CUDA(cudaMemcpyAsync(h, ctr.ptr, sizeof h, cudaMemcpyDeviceToHost, s.stream));
         PB2_CUDA(cudaStreamSynchronize(s.stream));
         s.render_stats.nodes_visited = h[0], s.render_stats.prims_tested = h[1];
     } else {
-        k_trace_closest<false><<<trace_grid(n, 128), 128, 0, s.stream>>>(sv, rays, n, hit_tuvp, hit_inst, nullptr);
+        kernel_plain<<<trace_grid(n, 128), 128, 0, s.stream>>>(sv, io, s.trace_work.ptr, nullptr, s.refill_threshold);
         PB2_LAUNCH_CHECK();
     }
+}
+
+void trace_closest_dev(Scene &s, const float4 *rays, uint64_t n, float4 *hit_tuvp, int32_t *hit_inst) {
+    if (!s.bvh_valid) throw std::runtime_error("pb2_trace_closest: call pb2_bvh_build first");
+    if (!n) return;
+    ClosestIO io{ rays, hit_tuvp, hit_inst, s.d_prims.ptr, (uint32_t)n };
+    launch_trace(s, k_trace_closest<false>, k_trace_closest<true>, io, n);
 }
 void trace_any_dev(Scene &s, const float4 *rays, uint64_t n, uint32_t *occluded) {
     if (!s.bvh_valid) throw std::runtime_error("pb2_trace_any: call pb2_bvh_build first");
     if (!n) return;
-    const SceneView sv = s.view();
-    if (s.counting) {
-        DevBuf<unsigned long long> ctr(2);
-        ctr.zero(s.stream);
-        k_trace_any<true><<<trace_grid(n, 128), 128, 0, s.stream>>>(sv, rays, n, occluded, ctr.ptr);
-        PB2_LAUNCH_CHECK();
-        unsigned long long h[2];
-        PB2_CUDA(cudaMemcpyAsync(h, ctr.ptr, sizeof h, cudaMemcpyDeviceToHost, s.stream));
-        PB2_CUDA(cudaStreamSynchronize(s.stream));
-        s.render_stats.nodes_visited = h[0], s.render_stats.prims_tested = h[1];
-    } else {
-        k_trace_any<false><<<trace_grid(n, 128), 128, 0, s.stream>>>(sv, rays, n, occluded, nullptr);
-        PB2_LAUNCH_CHECK();
-    }
+    AnyIO io{ rays, occluded, (uint32_t)n };
+    launch_trace(s, k_trace_any<false>, k_trace_any<true>, io, n);
 }
 }// namespace pb2

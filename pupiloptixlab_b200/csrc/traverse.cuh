@@ -161,4 +161,150 @@ PB2_D bool traverse(const SceneView &sv, float3 o, float3 d, float tmin, RayHit 
     }
     return hit.prim_slot != 0xffffffffu;
 }
+
+// ---- persistent, dynamically refilled traversal ------------------------------------------------------------
+// The per-ray loop above leaves a warp waiting for its slowest ray (ncu, 30 M triangles, incoherent rays:
+// 5.8 of 32 threads active per instruction).  Here every lane owns a traversal state that survives across
+// rays and the warp advances in explicit lock step: per iteration every busy lane pops and tests ONE wide node
+// and then the primitives of the leaf slots it hit; finished lanes commit their result, and as soon as fewer
+// than `refill_threshold` lanes are still busy the idle lanes take the next rays from a global work counter
+// (one atomic per warp) — "persistent threads with replacement" (Aila & Laine 2009), with the difference
+// that the warp reconverges after every node step.  Measured on the 30 M-triangle terrain (profiles/):
+// letting lanes run ahead for 2 / 4 / 8 / 16 node steps between reconvergence points is 8 % / 22 % / 33 % /
+// 34 % slower than reconverging every step.
+//
+// IO supplies the rays and takes the results:
+//   uint32_t size() const;
+//   uint32_t load(uint32_t i, float3 &o, float3 &d, float &tmin, float &tmax) const;   returns a token (e.g. the path slot)
+//        that is handed back to commit()
+//   void commit(bool valid, uint32_t token, const RayHit &h, bool hit);
+//        called by ALL 32 lanes of the warp, converged, whenever at least one lane finished a ray
+//        (valid = this lane did), so implementations may use full-mask warp collectives
+#ifndef PB2_REFILL_THRESHOLD
+#define PB2_REFILL_THRESHOLD 26
+#endif
+
+struct RayState {
+    float3 o, d, idir;
+    float tmin;
+    RayHit hit;
+    uint2 G;           // current node group: (child base, hit bits 31..24 | imask 7..0)
+    uint32_t T;        // pending primitive bits of the current node
+    uint32_t prim_base;
+    uint32_t oct;
+    int sp;
+};
+
+PB2_D void ray_begin(RayState &r, float3 o, float3 d, float tmin, float tmax, bool empty_scene) {
+    auto safe_inv = [](float x) { return 1.f / (fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); };
+    r.o = o, r.d = d, r.tmin = tmin;
+    r.idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
+    r.oct = (r.idir.x >= 0.f ? 4u : 0u) | (r.idir.y >= 0.f ? 2u : 0u) | (r.idir.z >= 0.f ? 1u : 0u);
+    r.hit.t = tmax, r.hit.u = r.hit.v = 0.f, r.hit.prim_slot = 0xffffffffu;
+    r.G = make_uint2(0u, empty_scene ? 0u : 0x80000000u);
+    r.T = 0u, r.prim_base = 0u, r.sp = 0;
+}
+PB2_D bool ray_has_nodes(const RayState &r) { return (r.G.y & 0xff000000u) != 0u || r.sp > 0; }
+
+// pops the nearest pending internal node, tests its eight children, leaves the hit children in G / T
+PB2_D void node_step(const SceneView &sv, RayState &r, uint2 *stack) {
+    if (!(r.G.y & 0xff000000u)) r.G = stack[--r.sp];
+    const uint32_t bit = 31u - __clz(r.G.y);
+    r.G.y &= ~(1u << bit);
+    const uint32_t slot = (bit - 24u) ^ r.oct;
+    const uint32_t rel = __popc(r.G.y & 0xffu & ((1u << slot) - 1u));
+    const Bvh8Node *np = sv.nodes + (r.G.x + rel);
+    if (r.G.y & 0xff000000u) stack[r.sp++] = r.G;
+
+    const float4 n0 = __ldg(&np->n0);
+    const uint4 n1 = __ldg(&np->n1), n2 = __ldg(&np->n2), n3 = __ldg(&np->n3), n4 = __ldg(&np->n4);
+    const bool px = r.idir.x >= 0.f, py = r.idir.y >= 0.f, pz = r.idir.z >= 0.f;
+    const uint32_t oct4 = r.oct * 0x01010101u;
+    const uint32_t ebits = __float_as_uint(n0.w);
+    const float sx = __uint_as_float((ebits & 0xffu) << 23), sy = __uint_as_float(((ebits >> 8) & 0xffu) << 23),
+                sz = __uint_as_float(((ebits >> 16) & 0xffu) << 23);
+    const float3 adj = mk3(sx * r.idir.x, sy * r.idir.y, sz * r.idir.z);
+    const float3 org = mk3((n0.x - r.o.x) * r.idir.x, (n0.y - r.o.y) * r.idir.y, (n0.z - r.o.z) * r.idir.z);
+    constexpr float kFar = 1.0000004f; // far planes pushed out by a few ulps: rounding can never cull a touched box
+    const float3 adj_f = adj * kFar, org_f = org * kFar;
+    uint32_t hitmask = 0;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const uint32_t meta4 = half ? n1.w : n1.z;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+        const uint32_t bit_index4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;
+        const uint32_t qhx = half ? n3.w : n3.z, qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
+        const uint32_t nx = px ? qlx : qhx, fx = px ? qhx : qlx;
+        const uint32_t ny = py ? qly : qhy, fy = py ? qhy : qly;
+        const uint32_t nz = pz ? qlz : qhz, fz = pz ? qhz : qlz;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float tnx = (float)byte_of(nx, j) * adj.x + org.x, tfx = (float)byte_of(fx, j) * adj_f.x + org_f.x;
+            const float tny = (float)byte_of(ny, j) * adj.y + org.y, tfy = (float)byte_of(fy, j) * adj_f.y + org_f.y;
+            const float tnz = (float)byte_of(nz, j) * adj.z + org.z, tfz = (float)byte_of(fz, j) * adj_f.z + org_f.z;
+            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
+            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, r.hit.t));
+            if (tn <= tf) hitmask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
+        }
+    }
+    r.G = make_uint2(n1.x, (hitmask & 0xff000000u) | (ebits >> 24));
+    r.T = hitmask & 0x00ffffffu;
+    r.prim_base = n1.y;
+}
+
+template<bool ANY, bool COUNT, class IO>
+PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ work_counter, TraceCounters *ctr, int refill_threshold = PB2_REFILL_THRESHOLD) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    const uint32_t n = io.size();
+    const uint32_t lane = threadIdx.x & 31u;
+    uint2 stack[PB2_STACK_SIZE];
+    RayState r;
+    r.T = 0u, r.G = make_uint2(0u, 0u), r.sp = 0;
+    uint32_t ray = 0;
+    bool busy = false;
+    bool exhausted = false; // warp-uniform: the work counter has run past the end
+    for (;;) {              // every lane of the warp stays in this loop until the whole warp is done
+        // ---- refill: when fewer than `refill_threshold` lanes are busy, idle lanes take the next rays ----
+        const uint32_t busy_mask = __ballot_sync(kFull, busy);
+        if (!exhausted && __popc(busy_mask) < refill_threshold) {
+            const uint32_t idle = ~busy_mask;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
+            base = __shfl_sync(kFull, base, 0);
+            const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
+            if (!busy && mine < n) {
+                float3 o, d;
+                float tmin, tmax;
+                ray = io.load(mine, o, d, tmin, tmax);
+                ray_begin(r, o, d, tmin, tmax, sv.n_nodes == 0);
+                busy = true;
+            }
+            exhausted = base + __popc(idle) >= n;
+        } else if (busy_mask == 0u) {
+            break;
+        }
+        // ---- one node step, then the primitives it uncovered ----
+        if (busy && ray_has_nodes(r)) {
+            node_step(sv, r, stack);
+            if (COUNT) ++ctr->nodes;
+            while (r.T) {
+                const uint32_t i = __ffs(r.T) - 1;
+                r.T &= r.T - 1;
+                if (COUNT) ++ctr->prims;
+                if (intersect_prim(sv, r.prim_base + i, r.o, r.d, r.tmin, r.hit)) {
+                    if (ANY) r.T = 0u, r.G.y = 0u, r.sp = 0;
+                }
+            }
+        }
+        __syncwarp();
+        const bool done = busy && !ray_has_nodes(r);
+        if (__any_sync(kFull, done)) {
+            io.commit(done, ray, r.hit, r.hit.prim_slot != 0xffffffffu);
+            if (done) busy = false;
+        }
+    }
+}
 }// namespace pb2

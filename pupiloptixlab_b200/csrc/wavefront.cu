@@ -26,14 +26,12 @@ namespace pb2 {
 constexpr int kNumTypes = 8; // queue 0 = miss, 1..7 = EMatType
 constexpr int kCtrPerRound = 16;
 // per-round counter slots
-enum { CTR_EXT = 0, CTR_SHADOW = 1, CTR_MAT0 = 2 /* ..9 */ };
+enum { CTR_EXT = 0, CTR_SHADOW = 1, CTR_MAT0 = 2 /* ..9 */, CTR_WORK_EXT = 10, CTR_WORK_SHADOW = 11 };
 
 struct Wavefront {
     uint64_t capacity = 0;
-    DevBuf<float4> ray_o, ray_d, hit_tuvp, thr, rad, sh_o, sh_d, sh_c;
-    DevBuf<int32_t> hit_inst;
-    DevBuf<uint32_t> rng, state;
-    DevBuf<uint32_t> q_ext[2], q_shadow, q_mat;
+    DevBuf<float4> ray, hit, ps, shq; // 32-byte records per path slot (ray, hit, ps) and 48-byte shadow-queue entries (shq)
+    DevBuf<uint32_t> q_ext[2], q_mat;
     DevBuf<uint32_t> counters; // (max_depth + 2) rounds x kCtrPerRound
     DevBuf<unsigned long long> trav_counters, ray_totals;
     uint32_t rounds_alloc = 0;
@@ -50,9 +48,8 @@ struct Wavefront {
     void ensure(uint64_t paths, uint32_t rounds) {
         if (paths > capacity) {
             capacity = paths;
-            ray_o.alloc(paths), ray_d.alloc(paths), hit_tuvp.alloc(paths), thr.alloc(paths), rad.alloc(paths);
-            sh_o.alloc(paths), sh_d.alloc(paths), sh_c.alloc(paths), hit_inst.alloc(paths), rng.alloc(paths), state.alloc(paths);
-            q_ext[0].alloc(paths), q_ext[1].alloc(paths), q_shadow.alloc(paths), q_mat.alloc(paths * kNumTypes);
+            ray.alloc(paths * 2), hit.alloc(paths * 2), ps.alloc(paths * 2), shq.alloc(paths * 3);
+            q_ext[0].alloc(paths), q_ext[1].alloc(paths), q_mat.alloc(paths * kNumTypes);
         }
         if (rounds > rounds_alloc) {
             rounds_alloc = rounds;
@@ -73,11 +70,21 @@ void wavefront_destroy(Wavefront *wf) { delete wf; }
 
 namespace {
 
+// Path state lives in 32-byte records (one DRAM sector each) indexed by path slot p, so the scattered accesses
+// of the material-sorted shade kernel and of the dynamically scheduled trace kernels never pay for half-used
+// sectors; fields are grouped by WRITER so no kernel writes a partial record it has not read:
+//   ray[2p]   = o.xyz | bits(state: depth | lobe << 16)     ray[2p+1] = d.xyz | bsdf pdf      generate / shade
+//   hit[2p]   = t, u, v | bits(prim)                        hit[2p+1] = bits(inst), -, -, -   extend
+//   ps[2p]    = throughput.xyz | bits(rng)                  ps[2p+1]  = radiance.xyz | -      generate / shade (+ shadow: radiance half)
+// Shadow rays are created and consumed exactly once, so their payload travels with the queue instead:
+//   shq[3k]   = o.xyz | tmax      shq[3k+1] = d.xyz | bits(p)      shq[3k+2] = contribution.xyz | -
+// (extension rays always use tmin 1e-3 / tmax 1e16 and shadow rays tmin 1e-4: main.cu:82-83, emitter.h:93-96)
+// (Packing the three records of a slot into one 128-byte line was measured and is slower: -8 % Msamples/s, the
+// streaming kernels then stride over unused sectors; see profiles/README.md.)
 struct PathArrays {
-    float4 *ray_o, *ray_d, *hit_tuvp, *thr, *rad, *sh_o, *sh_d, *sh_c;
-    int32_t *hit_inst;
-    uint32_t *rng, *state;
+    float4 *ray, *hit, *ps, *shq;
 };
+constexpr float kExtendTmin = 0.001f, kExtendTmax = 1e16f, kShadowTmin = 0.0001f;
 struct FrameParams {
     uint32_t width, height, n_pixels;
     uint32_t max_depth;
@@ -125,74 +132,87 @@ __global__ void __launch_bounds__(256) k_generate(PathArrays pa, FrameParams fp,
         const float inv_len = 1.0f / sqrtf(dot(d, d));                                                              // :71
         d = make_float4(d.x * inv_len, d.y * inv_len, d.z * inv_len, 0.f);
         const float3 dir = normalize(mk3(dot(cam.c2w[0], d), dot(cam.c2w[1], d), dot(cam.c2w[2], d))); // :73
-        pa.ray_o[p] = make_float4(cam.c2w[0].w, cam.c2w[1].w, cam.c2w[2].w, 0.001f);                    // :75-78, tmin :82
-        pa.ray_d[p] = make_float4(dir.x, dir.y, dir.z, 1e16f);
-        pa.thr[p] = make_float4(1.f, 1.f, 1.f, 0.f);
-        pa.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
-        pa.rng[p] = rng;
-        pa.state[p] = 0u;
+        pa.ray[2 * (size_t)p] = make_float4(cam.c2w[0].w, cam.c2w[1].w, cam.c2w[2].w, __uint_as_float(0u)); // :75-78; state = depth 0
+        pa.ray[2 * (size_t)p + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
+        pa.ps[2 * (size_t)p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(rng));
+        pa.ps[2 * (size_t)p + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
         q_ext[p] = p;
     }
 }
 
-// ---- extend ------------------------------------------------------------------------------------------------
-template<bool COUNT>
-__global__ void __launch_bounds__(128) k_extend(SceneView sv, PathArrays pa, const uint32_t *__restrict__ q_in, const uint32_t *__restrict__ n_in,
-                                                uint32_t *__restrict__ q_mat, uint32_t *__restrict__ mat_counts, uint32_t capacity, int sort,
-                                                unsigned long long *__restrict__ trav) {
-    const uint32_t n = *n_in;
-    TraceCounters ctr{ 0, 0 };
-    // warp-uniform trip count so the queue append below runs with all 32 lanes converged
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + (threadIdx.x & 31u);
-        const bool valid = i < n;
-        uint32_t p = 0, type = 0;
+// ---- extend / shadow: persistent BVH8 traversal over an index queue (traverse.cuh) ----------------------------
+struct ExtendIO {
+    SceneView sv;
+    PathArrays pa;
+    const uint32_t *__restrict__ q_in;
+    uint32_t *__restrict__ q_mat, *__restrict__ mat_counts;
+    uint32_t n, capacity;
+    int sort;
+    PB2_D uint32_t size() const { return n; }
+    PB2_D uint32_t load(uint32_t i, float3 &o, float3 &d, float &tmin, float &tmax) const {
+        const uint32_t p = q_in[i];
+        const float4 ro = pa.ray[2 * (size_t)p], rd = pa.ray[2 * (size_t)p + 1];
+        o = mk3(ro), d = mk3(rd), tmin = kExtendTmin, tmax = kExtendTmax;
+        return p;
+    }
+    // writes the hit record and appends the path to the queue of the hit material type (0 = miss)
+    PB2_D void commit(bool valid, uint32_t p, const RayHit &h, bool hit) const {
+        uint32_t type = 0;
         if (valid) {
-            p = q_in[i];
-            const float4 ro = pa.ray_o[p], rd = pa.ray_d[p];
-            RayHit h;
-            h.t = rd.w, h.u = h.v = 0.f;
-            traverse<false, COUNT>(sv, mk3(ro), mk3(rd), ro.w, h, &ctr);
             int32_t inst = -1;
             uint32_t prim = 0;
-            if (h.prim_slot != 0xffffffffu) {
+            if (hit) {
                 const float4 *rec = reinterpret_cast<const float4 *>(sv.prims + h.prim_slot);
                 prim = __float_as_uint(__ldg(rec).w);
                 inst = (int32_t)__float_as_uint(__ldg(rec + 1).w);
                 type = (uint32_t)__ldg(&sv.instances[inst].mat_type) & 7u;
             }
-            pa.hit_tuvp[p] = make_float4(h.t, h.u, h.v, __uint_as_float(prim));
-            pa.hit_inst[p] = inst;
+            pa.hit[2 * (size_t)p] = make_float4(h.t, h.u, h.v, __uint_as_float(prim));
+            pa.hit[2 * (size_t)p + 1] = make_float4(__int_as_float(inst), 0.f, 0.f, 0.f);
             if (!sort) type = 1;
         }
-        __syncwarp();
         const uint32_t pos = warp_append_keyed(mat_counts, type, valid);
         if (valid) q_mat[(size_t)type * capacity + pos] = p;
     }
+};
+struct ShadowIO {
+    PathArrays pa;
+    uint32_t n;
+    PB2_D uint32_t size() const { return n; }
+    PB2_D uint32_t load(uint32_t i, float3 &o, float3 &d, float &tmin, float &tmax) const {
+        const float4 ro = pa.shq[3 * (size_t)i], rd = pa.shq[3 * (size_t)i + 1];
+        o = mk3(ro), d = mk3(rd), tmin = kShadowTmin, tmax = ro.w;
+        return i;
+    }
+    PB2_D void commit(bool valid, uint32_t i, const RayHit &, bool hit) const {
+        if (valid && !hit) { // main.cu:127 `if (!occluded)`
+            const uint32_t p = __float_as_uint(pa.shq[3 * (size_t)i + 1].w);
+            const float4 c = pa.shq[3 * (size_t)i + 2];
+            float4 r = pa.ps[2 * (size_t)p + 1];
+            r.x += c.x, r.y += c.y, r.z += c.z;
+            pa.ps[2 * (size_t)p + 1] = r;
+        }
+    }
+};
+
+template<bool COUNT>
+__global__ void __launch_bounds__(128) k_extend(SceneView sv, PathArrays pa, const uint32_t *__restrict__ q_in, const uint32_t *__restrict__ n_in,
+                                                uint32_t *__restrict__ q_mat, uint32_t *__restrict__ mat_counts, uint32_t capacity, int sort,
+                                                uint32_t *__restrict__ work, unsigned long long *__restrict__ trav, int refill) {
+    ExtendIO io{ sv, pa, q_in, q_mat, mat_counts, *n_in, capacity, sort };
+    TraceCounters ctr{ 0, 0 };
+    trace_persistent<false, COUNT>(sv, io, work, &ctr, refill);
     if (COUNT) {
         atomicAdd(&trav[0], (unsigned long long)ctr.nodes);
         atomicAdd(&trav[1], (unsigned long long)ctr.prims);
     }
 }
-
-// ---- shadow ------------------------------------------------------------------------------------------------
 template<bool COUNT>
-__global__ void __launch_bounds__(128) k_shadow(SceneView sv, PathArrays pa, const uint32_t *__restrict__ q_in, const uint32_t *__restrict__ n_in,
-                                                unsigned long long *__restrict__ trav) {
-    const uint32_t n = *n_in;
+__global__ void __launch_bounds__(128) k_shadow(SceneView sv, PathArrays pa, const uint32_t *__restrict__ n_in, uint32_t *__restrict__ work,
+                                                unsigned long long *__restrict__ trav, int refill) {
+    ShadowIO io{ pa, *n_in };
     TraceCounters ctr{ 0, 0 };
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t p = q_in[i];
-        const float4 ro = pa.sh_o[p], rd = pa.sh_d[p];
-        RayHit h;
-        h.t = rd.w, h.u = h.v = 0.f;
-        if (!traverse<true, COUNT>(sv, mk3(ro), mk3(rd), ro.w, h, &ctr)) { // main.cu:127 `if (!occluded)`
-            const float4 c = pa.sh_c[p];
-            float4 r = pa.rad[p];
-            r.x += c.x, r.y += c.y, r.z += c.z;
-            pa.rad[p] = r;
-        }
-    }
+    trace_persistent<true, COUNT>(sv, io, work, &ctr, refill);
     if (COUNT) {
         atomicAdd(&trav[2], (unsigned long long)ctr.nodes);
         atomicAdd(&trav[3], (unsigned long long)ctr.prims);
@@ -238,25 +258,30 @@ __device__ __forceinline__ void hit_local_geometry(const DevInstance *in, uint32
 
 // ---- shade -------------------------------------------------------------------------------------------------
 struct ShadeOut {
-    uint32_t *q_ext, *n_ext, *q_shadow, *n_shadow;
+    uint32_t *q_ext, *n_ext, *n_shadow;
     float *albedo, *normal, *test; // AOVs (may be null); written by the last frame of the batch only
     uint32_t write_aov_frame;      // frame index (within the batch) whose primary hits write the AOVs; ~0u = none
 };
 
-// One path at one hit (or miss).  Returns bit 0: a shadow ray was written, bit 1: an extension ray was written.
-__device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathArrays &pa, const FrameParams &fp, const ShadeOut &out, uint32_t p) {
-    const float4 hit = pa.hit_tuvp[p];
-    const int32_t inst = pa.hit_inst[p];
-    const float4 ro4 = pa.ray_o[p], rd4 = pa.ray_d[p];
+// A shadow ray produced by shade_path; it is appended to the shadow queue by the caller (warp-aggregated).
+struct ShadowRay {
+    float3 o, d, contrib;
+    float tmax;
+};
+// One path at one hit (or miss).  Returns bit 0: `sh` holds a shadow ray, bit 1: an extension ray was written.
+__device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathArrays &pa, const FrameParams &fp, const ShadeOut &out, uint32_t p, ShadowRay &sh) {
+    const float4 hit = pa.hit[2 * (size_t)p];
+    const int32_t inst = __float_as_int(pa.hit[2 * (size_t)p + 1].x);
+    const float4 ro4 = pa.ray[2 * (size_t)p], rd4 = pa.ray[2 * (size_t)p + 1];
     const float3 ray_o = mk3(ro4), ray_d = mk3(rd4);
-    const float4 thr4 = pa.thr[p];
+    const float4 thr4 = pa.ps[2 * (size_t)p], rad4 = pa.ps[2 * (size_t)p + 1];
     float3 throughput = mk3(thr4);
-    const float bsdf_pdf = thr4.w;
-    const uint32_t st = pa.state[p];
+    const float bsdf_pdf = rd4.w;
+    const uint32_t st = __float_as_uint(ro4.w);
     uint32_t depth = st & 0xffffu;
     const uint32_t sampled_type = st >> 16;
-    uint32_t rng = pa.rng[p];
-    float3 radiance = mk3(pa.rad[p]);
+    uint32_t rng = __float_as_uint(thr4.w);
+    float3 radiance = mk3(rad4);
     const uint32_t frame = p / fp.n_pixels, pixel = p - frame * fp.n_pixels;
     const bool write_aov = depth == 0 && frame == out.write_aov_frame;
 
@@ -275,7 +300,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
             env_radiance *= throughput * mis;
         }
         radiance += env_radiance; // :188
-        pa.rad[p] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
+        pa.ps[2 * (size_t)p + 1] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
         return 0u;
     }
 
@@ -319,8 +344,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
         else throughput /= rr;
     }
     if (!alive) {
-        pa.rad[p] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
-        pa.rng[p] = rng;
+        pa.ps[2 * (size_t)p + 1] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
         return 0u;
     }
     const Onb frame_onb(geo.normal);
@@ -347,9 +371,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
                         const float mis = es.is_delta ? 1.f : mis_weight(es.pdf, rec.pdf);
                         const float pdf_e = es.pdf * __ldg(&em->select_probability);
                         const float3 contrib = throughput * es.radiance * rec.f * NoL * mis / pdf_e;
-                        pa.sh_o[p] = make_float4(geo.position.x, geo.position.y, geo.position.z, 0.0001f);
-                        pa.sh_d[p] = make_float4(es.wi.x, es.wi.y, es.wi.z, es.distance - 0.0001f);
-                        pa.sh_c[p] = make_float4(contrib.x, contrib.y, contrib.z, 0.f);
+                        sh.o = geo.position, sh.d = es.wi, sh.tmax = es.distance - 0.0001f, sh.contrib = contrib;
                         emitted |= 1u;
                     }
                 }
@@ -364,19 +386,20 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
         if (!(is_zero(rec.f * fabsf(rec.wi.z)) || is_zero(rec.pdf))) {
             throughput *= rec.f * fabsf(rec.wi.z) / rec.pdf;
             const float3 dir = frame_onb.to_world(rec.wi);
-            pa.ray_o[p] = make_float4(geo.position.x, geo.position.y, geo.position.z, 0.001f);
-            pa.ray_d[p] = make_float4(dir.x, dir.y, dir.z, 1e16f);
-            pa.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, rec.pdf);
-            pa.state[p] = depth | (rec.type << 16);
+            pa.ray[2 * (size_t)p] = make_float4(geo.position.x, geo.position.y, geo.position.z, __uint_as_float(depth | (rec.type << 16)));
+            pa.ray[2 * (size_t)p + 1] = make_float4(dir.x, dir.y, dir.z, rec.pdf);
+            pa.ps[2 * (size_t)p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(rng));
             emitted |= 2u;
         }
     }
-    pa.rad[p] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
-    pa.rng[p] = rng;
+    pa.ps[2 * (size_t)p + 1] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
     return emitted;
 }
 
-__global__ void __launch_bounds__(128) k_shade(SceneView sv, PathArrays pa, FrameParams fp, const uint32_t *__restrict__ q_mat,
+// MINB = resident CTAs per SM the register allocator must allow: 4 -> 114 registers, no spills; 6 -> 80 registers,
+// 44 B of spills; 8 -> 64 registers, 160 B of spills.  The choice is measured, see profiles/.
+template<int MINB>
+__global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa, FrameParams fp, const uint32_t *__restrict__ q_mat,
                                                const uint32_t *__restrict__ mat_counts, uint32_t capacity, ShadeOut out) {
     // queue t occupies the virtual index range [start_t, start_t + round_up(count_t, 32)): a warp never
     // straddles two material types
@@ -392,13 +415,18 @@ __global__ void __launch_bounds__(128) k_shade(SceneView sv, PathArrays pa, Fram
         for (int k = 1; k < kNumTypes; ++k) t += vi >= start[k] ? 1 : 0;
         const uint32_t local = vi - start[t];
         uint32_t emitted = 0, p = 0;
+        ShadowRay sh;
         if (local < mat_counts[t]) {
             p = q_mat[(size_t)t * capacity + local];
-            emitted = shade_path(sv, pa, fp, out, p);
+            emitted = shade_path(sv, pa, fp, out, p, sh);
         }
         __syncwarp();
         const uint32_t ps = warp_append(out.n_shadow, emitted & 1u);
-        if (emitted & 1u) out.q_shadow[ps] = p;
+        if (emitted & 1u) { // consecutive lanes write consecutive 48-byte queue entries
+            pa.shq[3 * (size_t)ps] = make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax);
+            pa.shq[3 * (size_t)ps + 1] = make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(p));
+            pa.shq[3 * (size_t)ps + 2] = make_float4(sh.contrib.x, sh.contrib.y, sh.contrib.z, 0.f);
+        }
         const uint32_t pe = warp_append(out.n_ext, emitted & 2u);
         if (emitted & 2u) out.q_ext[pe] = p;
     }
@@ -422,7 +450,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4 *__restrict__ r
         float3 acc = (mode != 0 && (sample_cnt0 > 0 || mode == 2)) ? mk3(accum[px]) : mk3(0.f);
         float w = mode == 2 ? accum[px].w : 1.f;
         for (uint32_t f = 0; f < frames; ++f) {
-            const float3 r = mk3(rad[(size_t)f * n_pixels + px]);
+            const float3 r = mk3(rad[2 * ((size_t)f * n_pixels + px) + 1]); // radiance half of the ps record
             if (mode == 2) { // plain sum for sample-sharded multi-GPU rendering
                 acc += r;
                 w += 1.f;
@@ -476,8 +504,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const SceneView sv = s.view();
-    PathArrays pa{ wf.ray_o.ptr, wf.ray_d.ptr, wf.hit_tuvp.ptr, wf.thr.ptr, wf.rad.ptr, wf.sh_o.ptr, wf.sh_d.ptr, wf.sh_c.ptr,
-                   wf.hit_inst.ptr, wf.rng.ptr, wf.state.ptr };
+    PathArrays pa{ wf.ray.ptr, wf.hit.ptr, wf.ps.ptr, wf.shq.ptr };
 
     for (auto &e : wf.events) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
     wf.events.clear();
@@ -521,23 +548,25 @@ void render(Scene &s, const pb2_launch_params &lp) {
             stage_begin(1);
             if (s.counting)
                 k_extend<true><<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity,
-                                                            s.sort_by_material ? 1 : 0, wf.trav_counters.ptr);
+                                                            s.sort_by_material ? 1 : 0, ctr + CTR_WORK_EXT, wf.trav_counters.ptr, s.refill_threshold);
             else
                 k_extend<false><<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity,
-                                                             s.sort_by_material ? 1 : 0, nullptr);
+                                                             s.sort_by_material ? 1 : 0, ctr + CTR_WORK_EXT, nullptr, s.refill_threshold);
             PB2_LAUNCH_CHECK();
             stage_end();
-            ShadeOut so{ q_out, ctr_next + CTR_EXT, wf.q_shadow.ptr, ctr + CTR_SHADOW, (float *)lp.albedo_buffer, (float *)lp.normal_buffer,
+            ShadeOut so{ q_out, ctr_next + CTR_EXT, ctr + CTR_SHADOW, (float *)lp.albedo_buffer, (float *)lp.normal_buffer,
                          (float *)lp.test_buffer, last_batch ? frames - 1 : ~0u };
             stage_begin(2);
-            k_shade<<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
+            if (s.shade_variant == 4) k_shade<4><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
+            else if (s.shade_variant == 8) k_shade<8><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
+            else k_shade<6><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
             PB2_LAUNCH_CHECK();
             stage_end();
             wf.launches += 2, ++wf.n_extend, ++wf.n_shade;
             if (r + 1 < rounds) { // the last round cannot emit rays (depth >= max_depth)
                 stage_begin(3);
-                if (s.counting) k_shadow<true><<<grid_trace, 128, 0, st>>>(sv, pa, wf.q_shadow.ptr, ctr + CTR_SHADOW, wf.trav_counters.ptr);
-                else k_shadow<false><<<grid_trace, 128, 0, st>>>(sv, pa, wf.q_shadow.ptr, ctr + CTR_SHADOW, nullptr);
+                if (s.counting) k_shadow<true><<<grid_trace, 128, 0, st>>>(sv, pa, ctr + CTR_SHADOW, ctr + CTR_WORK_SHADOW, wf.trav_counters.ptr, s.refill_threshold);
+                else k_shadow<false><<<grid_trace, 128, 0, st>>>(sv, pa, ctr + CTR_SHADOW, ctr + CTR_WORK_SHADOW, nullptr, s.refill_threshold);
                 PB2_LAUNCH_CHECK();
                 stage_end();
                 ++wf.launches, ++wf.n_shadow;
@@ -545,7 +574,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
         }
         stage_begin(4);
         k_accumulate<<<(unsigned)std::min<uint64_t>((n_pixels + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>(
-            wf.rad.ptr, n_pixels, frames, lp.accumulate, sample_cnt, (float4 *)lp.accum_buffer, (float4 *)lp.frame_buffer);
+            wf.ps.ptr, n_pixels, frames, lp.accumulate, sample_cnt, (float4 *)lp.accum_buffer, (float4 *)lp.frame_buffer);
         PB2_LAUNCH_CHECK();
         stage_end();
         ++wf.launches;

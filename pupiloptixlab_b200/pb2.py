@@ -248,6 +248,10 @@ class Scene:
         check(lib().pb2_render_stats_get(self.h, C.byref(st)))
         return st
 
+    def render_stats_raw(self) -> RenderStats:
+        """counters of the last pb2_trace_* call (no render needed)"""
+        return self.render_stats()
+
     def finalize_sum(self, sum_ptr: int, frame_ptr: int, n_pixels: int, total_spp: int):
         check(lib().pb2_finalize_sum(self.h, C.c_void_p(sum_ptr), C.c_void_p(frame_ptr), n_pixels, total_spp))
 

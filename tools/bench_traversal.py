@@ -1,0 +1,156 @@
+#!/usr/bin/env python
+"""Config C4 (BASELINE.json configs[3]): GPU BVH build time and BVH8 traversal throughput on the ~30 M-triangle
+procedural terrain, with the traversal kernels' memory roofline from their own node / primitive counters.
+
+    python tools/bench_traversal.py [--n 3873] [--rays 2097152] [--builder 0|1] [--reps 5]
+
+Ray batches: (i) 1080p primary camera rays, (ii) incoherent cosine-bounce rays leaving the primary hit
+points, (iii) shadow rays from the hit points to the area light.  Prints one JSON line per batch plus one for the build.
+Rays are resident in HBM; timing = CUDA events around `reps` launches of pb2_trace_*_dev on torch's stream.
+"""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def camera_rays(s2c, c2w, w, h, seed=0):
+    rng = np.random.default_rng(seed)
+    ys, xs = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+    u = (xs + rng.random((h, w), dtype=np.float32)) / np.float32(w)
+    v = (ys + rng.random((h, w), dtype=np.float32)) / np.float32(h)
+    pf = np.stack([u, v, np.zeros_like(u), np.ones_like(u)], -1).reshape(-1, 4)
+    d = pf @ s2c.T
+    d = d[:, :3] / d[:, 3:4]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    dw = d @ c2w[:3, :3].T
+    dw /= np.linalg.norm(dw, axis=1, keepdims=True)
+    rays = np.zeros((w * h, 8), np.float32)
+    rays[:, 0:3], rays[:, 3], rays[:, 4:7], rays[:, 7] = c2w[:3, 3], 1e-3, dw, 1e16
+    return rays
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=3873)
+    ap.add_argument("--rays", type=int, default=1 << 21)
+    ap.add_argument("--builder", type=int, default=-1)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--refill", type=str, default="", help="comma list of refill thresholds to sweep")
+    args = ap.parse_args()
+    import torch
+    from pupiloptixlab_b200 import pupil, scenes
+    peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"] if (ROOT / "MEASURED_PEAKS.json").exists() else 6650.0
+
+    t0 = time.perf_counter()
+    desc = scenes.terrain(args.n, args.width, args.height, 8)
+    t_gen = time.perf_counter() - t0
+    pupil.init(0)
+    if args.builder >= 0:
+        pupil.set_bvh_builder(args.builder)
+    t0 = time.perf_counter()
+    pupil.load_scene(desc)
+    scene = pupil.scene_handle()
+    t_load = time.perf_counter() - t0
+    bs = pupil.build_stats()
+    builds = [bs.build_ms]
+    for _ in range(2):  # rebuild twice more: steady-state build time (allocator warm)
+        pupil.set_bvh_builder(args.builder if args.builder >= 0 else 1)
+        builds.append(pupil.build_stats().build_ms)
+    scene = pupil.scene_handle()
+    tri_bytes = bs.n_triangles * 230
+    print(json.dumps({"what": "bvh_build", "n_prims": bs.n_prims, "n_nodes": bs.n_nodes, "bvh_bytes": bs.bvh_bytes, "build_ms": min(builds),
+                      "build_ms_all": builds, "mtris_per_s": bs.n_triangles / min(builds) / 1e3, "sah_cost": bs.sah_cost, "depth": bs.max_depth,
+                      "roofline": {"bound": "hbm", "achieved": tri_bytes / (min(builds) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": tri_bytes / (min(builds) * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_triangle": 230},
+                      "scene_generate_s": t_gen, "scene_load_s": t_load}), flush=True)
+
+    stream = torch.cuda.Stream()
+    scene.set_stream(stream.cuda_stream)
+    s2c, c2w, _ = pupil.camera()
+    prim = camera_rays(s2c, c2w, args.width, args.height)
+
+    def trace(rays_np, any_hit, label):
+        n = len(rays_np)
+        rays = torch.from_numpy(rays_np).cuda()
+        tuvp = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+        inst = torch.zeros(n, dtype=torch.int32, device="cuda")
+        occ = torch.zeros(n, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+
+        def launch():
+            if any_hit:
+                scene.trace_any_dev(rays.data_ptr(), n, occ.data_ptr())
+            else:
+                scene.trace_closest_dev(rays.data_ptr(), n, tuvp.data_ptr(), inst.data_ptr())
+        for _ in range(3):
+            launch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(args.reps):
+                launch()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.reps
+        scene.set_option("counting", 1)
+        launch()
+        scene.synchronize()
+        st = scene.render_stats_raw()
+        scene.set_option("counting", 0)
+        nodes, prims = st.nodes_visited, st.prims_tested
+        out_b = 4 if any_hit else 20
+        bytes_ = n * (32 + out_b) + nodes * 80 + prims * 48
+        hits = int((occ != 0).sum().item()) if any_hit else int((inst >= 0).sum().item())
+        print(json.dumps({"what": label, "rays": n, "ms": ms, "mrays_per_s": n / ms / 1e3, "hit_fraction": hits / n, "nodes_per_ray": nodes / n,
+                          "prims_per_ray": prims / n,
+                          "roofline": {"bound": "hbm", "achieved": bytes_ / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                       "frac": bytes_ / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_ray": bytes_ / n}}), flush=True)
+        return tuvp.cpu().numpy(), inst.cpu().numpy()
+
+    sweep = [tuple(int(y) for y in x.split(":")) for x in args.refill.split(",")] if args.refill else [None]
+
+    def apply(thr):
+        scene.set_option("refill_threshold", thr[0])
+
+    tuvp, inst = trace(prim, False, "closest_primary_1080p")
+    hit = inst >= 0
+    pos = prim[hit, 0:3] + tuvp[hit, 0:1] * prim[hit, 4:7]
+    rng = np.random.default_rng(7)
+    k = min(args.rays, len(pos))
+    sel = rng.choice(len(pos), k, replace=len(pos) < k)
+    p = pos[sel]
+    # cosine-distributed directions about +Y (the terrain is a height field)
+    u1, u2 = rng.random(k, dtype=np.float32), rng.random(k, dtype=np.float32)
+    r, phi = np.sqrt(u1), 2 * np.pi * u2
+    d = np.stack([r * np.cos(phi), np.sqrt(np.maximum(0, 1 - u1)), r * np.sin(phi)], -1).astype(np.float32)
+    inco = np.zeros((k, 8), np.float32)
+    inco[:, 0:3], inco[:, 3], inco[:, 4:7], inco[:, 7] = p, 1e-3, d, 1e16
+    inco = inco[rng.permutation(k)]
+    for thr in sweep:
+        if thr is not None:
+            apply(thr)
+            trace(prim, False, f"closest_primary_1080p thr={thr}")
+        trace(inco, False, f"closest_incoherent_bounce thr={thr}")
+    light = np.array([0.0, 12.0, 0.0], np.float32) + rng.uniform(-3, 3, (k, 3)).astype(np.float32) * np.array([1, 0, 1], np.float32)
+    dl = light - p
+    dist = np.linalg.norm(dl, axis=1, keepdims=True)
+    sh = np.zeros((k, 8), np.float32)
+    sh[:, 0:3], sh[:, 3], sh[:, 4:7], sh[:, 7] = p, 1e-4, dl / dist, dist[:, 0] - 1e-4
+    for thr in sweep:
+        if thr is not None:
+            apply(thr)
+        trace(sh, True, f"anyhit_shadow_to_light thr={thr}")
+    pupil.shutdown()
+
+
+if __name__ == "__main__":
+    main()
