@@ -179,7 +179,8 @@ int pb2_render(pb2_scene *scene, const pb2_launch_params *params);
 int pb2_synchronize(pb2_scene *scene);
 int pb2_render_stats_get(pb2_scene *scene, pb2_render_stats *stats); /* synchronises */
 /* options: profiling (per-stage events, serialises stages), counting (traversal counters),
- * paths_in_flight (0 = default), sort_by_material (default 1) */
+ * paths_in_flight (0 = default), sort_by_material (1 on, 0 off, -1 = auto: on when the scene has more than one
+ * material type; default -1), refill_threshold (persistent traversal), shade_variant (4 | 6 resident CTAs per SM) */
 int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value);
 /* multi-GPU shards render with accumulate = 2 (sum); after the cross-GPU reduction the root calls this:
  * frame[i] = (sum[i].xyz / total_spp, 1).   */

@@ -48,6 +48,9 @@ Scene::~Scene() {
 }
 void Scene::upload_tables() {
     if (!tables_dirty) return;
+    uint32_t seen = 0;
+    for (const DevInstance &in : h_inst) seen |= 1u << (in.mat_type & 7);
+    n_material_types = __builtin_popcount(seen);
     d_inst.upload(h_inst.data(), h_inst.size(), stream);
     d_mat.upload(h_mat.data(), h_mat.size(), stream);
     d_areas.upload(h_areas.data(), h_areas.size(), stream);
@@ -364,7 +367,7 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     const std::string n = name;
     if (n == "profiling") s.profiling = value != 0;
     else if (n == "counting") s.counting = value != 0;
-    else if (n == "sort_by_material") s.sort_by_material = value != 0;
+    else if (n == "sort_by_material") s.sort_by_material = value < 0 ? -1 : (value != 0);
     else if (n == "refill_threshold") s.refill_threshold = (int)std::min<int64_t>(33, std::max<int64_t>(0, value));
     else if (n == "shade_variant") s.shade_variant = (int)value;
     else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);

@@ -40,7 +40,9 @@ struct Scene {
     pb2_build_stats build_stats{};
 
     // options
-    bool profiling = false, counting = false, sort_by_material = true;
+    bool profiling = false, counting = false;
+    int sort_by_material = -1;  // 1 on, 0 off, -1 auto (on when the scene has more than one material type)
+    int n_material_types = 0;   // distinct EMatType values among the instances (upload_tables)
     uint64_t paths_in_flight = 0;
     int refill_threshold = 26;
     int shade_variant = 6;     // k_shade<MINB>: 4, 6 or 8 resident CTAs per SM // persistent traversal: refill idle lanes when fewer than this many are busy

@@ -169,10 +169,10 @@ struct ExtendIO {
             }
             pa.hit[2 * (size_t)p] = make_float4(h.t, h.u, h.v, __uint_as_float(prim));
             pa.hit[2 * (size_t)p + 1] = make_float4(__int_as_float(inst), 0.f, 0.f, 0.f);
-            if (!sort) type = 1;
         }
-        const uint32_t pos = warp_append_keyed(mat_counts, type, valid);
-        if (valid) q_mat[(size_t)type * capacity + pos] = p;
+        // no queue work here: rays finish in scheduling order, and appending in that order would scatter the next
+        // kernel's path-state accesses.  k_bin (sorted mode) or k_shade itself (unsorted) walk the queue in order.
+        (void)type;
     }
 };
 struct ShadowIO {
@@ -396,38 +396,108 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
     return emitted;
 }
 
+// ---- bin: stable split of the extension queue into the eight per-material queues ------------------------------
+// Walks the queue in order and keeps that order inside every material queue (per CTA slice of 256 entries; one
+// atomic per present type per CTA), so k_shade's scattered record accesses stay ascending in the path slot.
+__global__ void __launch_bounds__(256) k_bin(SceneView sv, PathArrays pa, const uint32_t *__restrict__ q_in, const uint32_t *__restrict__ n_in,
+                                             uint32_t *__restrict__ q_mat, uint32_t *__restrict__ mat_counts, uint32_t capacity) {
+    __shared__ uint32_t s_cnt[8][kNumTypes], s_base[kNumTypes];
+    const uint32_t n = *n_in, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t total = (n + 255u) & ~255u;
+    for (uint32_t i = blockIdx.x * 256u + threadIdx.x; i < total; i += gridDim.x * 256u) {
+        if (threadIdx.x < 8 * kNumTypes) (&s_cnt[0][0])[threadIdx.x] = 0u;
+        __syncthreads();
+        const bool valid = i < n;
+        uint32_t p = 0, type = kNumTypes;
+        if (valid) {
+            p = q_in[i];
+            const int32_t inst = __float_as_int(pa.hit[2 * (size_t)p + 1].x);
+            type = inst < 0 ? 0u : ((uint32_t)__ldg(&sv.instances[inst].mat_type) & 7u);
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, type);
+        const uint32_t rank = __popc(peers & lanemask_lt());
+        if (valid && rank == 0) s_cnt[warp][type] = __popc(peers);
+        __syncthreads();
+        if (threadIdx.x < kNumTypes) {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t c = s_cnt[w][threadIdx.x];
+                s_cnt[w][threadIdx.x] = run;
+                run += c;
+            }
+            s_base[threadIdx.x] = run ? atomicAdd(&mat_counts[threadIdx.x], run) : 0u;
+        }
+        __syncthreads();
+        if (valid) q_mat[(size_t)type * capacity + s_base[type] + s_cnt[warp][type] + rank] = p;
+        __syncthreads();
+    }
+}
+
+// Order-preserving append of a 128-thread CTA to two queues at once: thread order is kept inside the CTA's slice
+// (a CTA works on 128 consecutive queue entries, so runs of ascending path slots survive compaction and the next
+// kernel's record accesses stay close to sequential), one atomic per queue per CTA.
+__device__ __forceinline__ void block_append2(uint32_t *counter_a, uint32_t *counter_b, bool pred_a, bool pred_b, uint32_t &pos_a, uint32_t &pos_b) {
+    __shared__ uint32_t s_cnt[2][4], s_base[2];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t ma = __ballot_sync(0xffffffffu, pred_a), mb = __ballot_sync(0xffffffffu, pred_b);
+    if (lane == 0) s_cnt[0][warp] = __popc(ma), s_cnt[1][warp] = __popc(mb);
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t c = s_cnt[threadIdx.x][w];
+            s_cnt[threadIdx.x][w] = run;
+            run += c;
+        }
+        s_base[threadIdx.x] = run ? atomicAdd(threadIdx.x ? counter_b : counter_a, run) : 0u;
+    }
+    __syncthreads();
+    pos_a = s_base[0] + s_cnt[0][warp] + __popc(ma & lanemask_lt());
+    pos_b = s_base[1] + s_cnt[1][warp] + __popc(mb & lanemask_lt());
+    __syncthreads(); // s_cnt / s_base are reused by the next iteration
+}
+
 // MINB = resident CTAs per SM the register allocator must allow: 4 -> 114 registers, no spills; 6 -> 80 registers,
 // 44 B of spills; 8 -> 64 registers, 160 B of spills.  The choice is measured, see profiles/.
-template<int MINB>
-__global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa, FrameParams fp, const uint32_t *__restrict__ q_mat,
-                                               const uint32_t *__restrict__ mat_counts, uint32_t capacity, ShadeOut out) {
-    // queue t occupies the virtual index range [start_t, start_t + round_up(count_t, 32)): a warp never
-    // straddles two material types
+// SORTED: paths come from the eight per-material queues filled by k_extend (queue t occupies the virtual index
+// range [start_t, start_t + round_up(count_t, 128)): a CTA never straddles two material types); otherwise the
+// kernel walks the extension queue itself, in order, and branches on the material per path.
+template<int MINB, bool SORTED>
+__global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa, FrameParams fp, const uint32_t *__restrict__ queue,
+                                               const uint32_t *__restrict__ counts, uint32_t capacity, ShadeOut out) {
     uint32_t start[kNumTypes + 1];
     start[0] = 0;
+    if (SORTED) {
 #pragma unroll
-    for (int t = 0; t < kNumTypes; ++t) start[t + 1] = start[t] + ((mat_counts[t] + 31u) & ~31u);
-    const uint32_t total = start[kNumTypes];
+        for (int t = 0; t < kNumTypes; ++t) start[t + 1] = start[t] + ((counts[t] + 127u) & ~127u);
+    }
+    const uint32_t total = SORTED ? start[kNumTypes] : ((counts[0] + 127u) & ~127u);
 
-    for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total; vi += gridDim.x * blockDim.x) { // total % 32 == 0: warp-uniform
-        int t = 0;
-#pragma unroll
-        for (int k = 1; k < kNumTypes; ++k) t += vi >= start[k] ? 1 : 0;
-        const uint32_t local = vi - start[t];
+    for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total; vi += gridDim.x * blockDim.x) { // total % 128 == 0: CTA-uniform
         uint32_t emitted = 0, p = 0;
         ShadowRay sh;
-        if (local < mat_counts[t]) {
-            p = q_mat[(size_t)t * capacity + local];
-            emitted = shade_path(sv, pa, fp, out, p, sh);
+        bool valid;
+        if (SORTED) {
+            int t = 0;
+#pragma unroll
+            for (int k = 1; k < kNumTypes; ++k) t += vi >= start[k] ? 1 : 0;
+            const uint32_t local = vi - start[t];
+            valid = local < counts[t];
+            if (valid) p = queue[(size_t)t * capacity + local];
+        } else {
+            valid = vi < counts[0];
+            if (valid) p = queue[vi];
         }
-        __syncwarp();
-        const uint32_t ps = warp_append(out.n_shadow, emitted & 1u);
-        if (emitted & 1u) { // consecutive lanes write consecutive 48-byte queue entries
+        if (valid) emitted = shade_path(sv, pa, fp, out, p, sh);
+        uint32_t ps, pe;
+        block_append2(out.n_shadow, out.n_ext, emitted & 1u, emitted & 2u, ps, pe);
+        if (emitted & 1u) { // consecutive threads write consecutive 48-byte queue entries
             pa.shq[3 * (size_t)ps] = make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax);
             pa.shq[3 * (size_t)ps + 1] = make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(p));
             pa.shq[3 * (size_t)ps + 2] = make_float4(sh.contrib.x, sh.contrib.y, sh.contrib.z, 0.f);
         }
-        const uint32_t pe = warp_append(out.n_ext, emitted & 2u);
         if (emitted & 2u) out.q_ext[pe] = p;
     }
 }
@@ -504,6 +574,8 @@ void render(Scene &s, const pb2_launch_params &lp) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const SceneView sv = s.view();
+    // material sorting pays when shading diverges: on by default only for scenes with more than one material type
+    const bool sorted = s.sort_by_material == 1 || (s.sort_by_material < 0 && s.n_material_types > 1);
     PathArrays pa{ wf.ray.ptr, wf.hit.ptr, wf.ps.ptr, wf.shq.ptr };
 
     for (auto &e : wf.events) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
@@ -531,7 +603,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
                         lp.seed_stride ? lp.seed_stride : 1u, frames };
         const unsigned grid_stream = (unsigned)std::min<uint64_t>((n_paths + 255) / 256, (uint64_t)sms * 8);
         const unsigned grid_trace = (unsigned)std::min<uint64_t>((n_paths + 127) / 128, (uint64_t)sms * 16);
-        const unsigned grid_shade = (unsigned)std::min<uint64_t>((n_paths + kNumTypes * 32 + 127) / 128, (uint64_t)sms * 12);
+        const unsigned grid_shade = (unsigned)std::min<uint64_t>((n_paths + kNumTypes * 128 + 127) / 128, (uint64_t)sms * 12);
 
         PB2_CUDA(cudaMemsetAsync(wf.counters.ptr, 0, wf.counters.bytes(), st));
         stage_begin(0);
@@ -548,18 +620,29 @@ void render(Scene &s, const pb2_launch_params &lp) {
             stage_begin(1);
             if (s.counting)
                 k_extend<true><<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity,
-                                                            s.sort_by_material ? 1 : 0, ctr + CTR_WORK_EXT, wf.trav_counters.ptr, s.refill_threshold);
+                                                            sorted ? 1 : 0, ctr + CTR_WORK_EXT, wf.trav_counters.ptr, s.refill_threshold);
             else
                 k_extend<false><<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity,
-                                                             s.sort_by_material ? 1 : 0, ctr + CTR_WORK_EXT, nullptr, s.refill_threshold);
+                                                             sorted ? 1 : 0, ctr + CTR_WORK_EXT, nullptr, s.refill_threshold);
             PB2_LAUNCH_CHECK();
             stage_end();
+            if (sorted) {
+                stage_begin(2);
+                k_bin<<<grid_stream, 256, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity);
+                PB2_LAUNCH_CHECK();
+                stage_end();
+                ++wf.launches;
+            }
             ShadeOut so{ q_out, ctr_next + CTR_EXT, ctr + CTR_SHADOW, (float *)lp.albedo_buffer, (float *)lp.normal_buffer,
                          (float *)lp.test_buffer, last_batch ? frames - 1 : ~0u };
             stage_begin(2);
-            if (s.shade_variant == 4) k_shade<4><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
-            else if (s.shade_variant == 8) k_shade<8><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
-            else k_shade<6><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
+            if (sorted) {
+                if (s.shade_variant == 4) k_shade<4, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
+                else k_shade<6, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
+            } else {
+                if (s.shade_variant == 4) k_shade<4, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so);
+                else k_shade<6, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so);
+            }
             PB2_LAUNCH_CHECK();
             stage_end();
             wf.launches += 2, ++wf.n_extend, ++wf.n_shade;
