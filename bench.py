@@ -198,7 +198,7 @@ def main():
         return run_reference_impl(args)
 
     import torch
-    from pupiloptixlab_b200 import pb2, pupil
+    from pupiloptixlab_b200 import pb2, pupil, shard
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -206,6 +206,7 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3)
@@ -231,14 +232,14 @@ def main():
     accum_t = torch.as_tensor(DevPtr(accum_ptr, n_px * 4), device=f"cuda:{local}") if world > 1 else None
 
     def step(i: int):
-        # rank r renders seeds r + (i*spp + k)*world, k = 0..spp-1
-        pupil.pass_config(frames_per_run=spp, first_seed=rank + i * spp * world, seed_stride=world, sum_mode=world > 1)
+        sp = shard.plan(rank, world, i, spp)  # rank r renders seeds i*spp*world + r + k*world, k = 0..spp-1
+        pupil.pass_config(frames_per_run=sp.spp, first_seed=sp.first_seed, seed_stride=sp.seed_stride, sum_mode=world > 1)
         pupil.run(1)
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.reduce(accum_t, dst=0, op=dist.ReduceOp.SUM)
+                shard.reduce_sums(accum_t, dist)
                 if rank == 0:
-                    scene.finalize_sum(accum_ptr, frame_ptr, n_px, spp * world)
+                    scene.finalize_sum(accum_ptr, frame_ptr, n_px, sp.total_spp)
 
     def barrier():
         torch.cuda.synchronize()
@@ -285,18 +286,19 @@ def main():
     roofline = None
     if rank == 0:
         scene.set_option("counting", 1)
-        pupil.pass_config(frames_per_run=spp, first_seed=rank + warmup * spp * world, seed_stride=world, sum_mode=world > 1)
+        sp = shard.plan(rank, world, warmup, spp)
+        pupil.pass_config(frames_per_run=sp.spp, first_seed=sp.first_seed, seed_stride=sp.seed_stride, sum_mode=world > 1)
         pupil.run(1)
         cs = pupil.render_stats()
         scene.set_option("counting", 0)
         nodes_c, prims_c = cs.nodes_visited - cs.nodes_shadow, cs.prims_tested - cs.prims_shadow
+        # DESIGN.md "Algorithmic bytes" (32-byte records: ray, hit, ps; 48-byte shadow-queue entries; 80 B / node, 48 B / primitive)
+        big_mesh = desc.num_triangles() * 36 > 64e6  # vertex data does not stay in L2: count the hit triangle's attributes per vertex
+        ext_rays = max(cs.closest_rays - n_px * spp, 0)  # extension rays emitted by k_shade (the rest are camera rays)
         per_step = {
-            # DESIGN.md "Algorithmic bytes": ray in 32 + queue index 4 + hit out 20 + queue slot 4; 80 B / node, 48 B / primitive
-            "extend": cs.closest_rays * (32 + 4 + 20 + 4) + nodes_c * 80 + prims_c * 48,
-            # ray in 32 + index 4 + (unoccluded: contribution 16 + radiance RMW 32 ~ counted for all) ; 80 / 48
-            "shadow": cs.shadow_rays * (32 + 4 + 48) + cs.nodes_shadow * 80 + cs.prims_shadow * 48,
-            # path state in 96 + radiance/rng out 20 + instance/material records 208 + vertex attributes 108 (+ 52 per emitted ray)
-            "shade": cs.closest_rays * (96 + 20 + 208 + 108) + (cs.shadow_rays + max(cs.closest_rays - n_px * spp, 0)) * 52,
+            "extend": cs.closest_rays * (4 + 32 + 32) + nodes_c * 80 + prims_c * 48,
+            "shadow": cs.shadow_rays * 32 + cs.shadow_unoccluded * (16 + 32 + 32) + cs.nodes_shadow * 80 + cs.prims_shadow * 48,
+            "shade": cs.closest_rays * (4 + 96 + 32 + (40 if cs.sorted else 0) + (108 if big_mesh else 0)) + ext_rays * 36 + cs.shadow_rays * 48,
         }
         dom = max(("extend", "shade", "shadow"), key=lambda k: stage[k])
         peak, peak_kind = load_peaks()

@@ -116,6 +116,9 @@ typedef struct pb2_render_stats {
     uint32_t batches, rounds;                                         /* wavefront batches executed, bounce rounds per batch */
     uint32_t extend_launches, shade_launches, shadow_launches, other_launches; /* kernel launches by stage */
     uint64_t shaded_paths;                                            /* path-vertex shading invocations (= closest rays traced) */
+    uint64_t shadow_unoccluded;                                       /* shadow rays that reached the light, only when counting is on */
+    uint32_t sorted;                                                  /* 1: material-sorted shading (k_bin ran), 0: in-order shading */
+    uint32_t pad0;
 } pb2_render_stats;
 
 /* ---- library / device ------------------------------------------------------------------------------- */

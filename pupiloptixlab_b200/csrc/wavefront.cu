@@ -43,7 +43,7 @@ struct Wavefront {
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     uint64_t launches = 0;
     uint32_t rounds_used = 0, batches = 0, n_extend = 0, n_shade = 0, n_shadow = 0;
-    bool stats_pending = false;
+    bool stats_pending = false, sorted = false;
 
     void ensure(uint64_t paths, uint32_t rounds) {
         if (paths > capacity) {
@@ -55,7 +55,7 @@ struct Wavefront {
             rounds_alloc = rounds;
             counters.alloc((size_t)rounds * kCtrPerRound);
         }
-        if (!trav_counters.ptr) trav_counters.alloc(4), ray_totals.alloc(2);
+        if (!trav_counters.ptr) trav_counters.alloc(8), ray_totals.alloc(2);
         if (!t0) {
             PB2_CUDA(cudaEventCreate(&t0));
             PB2_CUDA(cudaEventCreate(&t1));
@@ -178,6 +178,7 @@ struct ExtendIO {
 struct ShadowIO {
     PathArrays pa;
     uint32_t n;
+    unsigned long long *unoccluded; // counting mode only (roofline bookkeeping), else nullptr
     PB2_D uint32_t size() const { return n; }
     PB2_D uint32_t load(uint32_t i, float3 &o, float3 &d, float &tmin, float &tmax) const {
         const float4 ro = pa.shq[3 * (size_t)i], rd = pa.shq[3 * (size_t)i + 1];
@@ -191,6 +192,7 @@ struct ShadowIO {
             float4 r = pa.ps[2 * (size_t)p + 1];
             r.x += c.x, r.y += c.y, r.z += c.z;
             pa.ps[2 * (size_t)p + 1] = r;
+            if (unoccluded) atomicAdd(unoccluded, 1ull);
         }
     }
 };
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(128) k_extend(SceneView sv, PathArrays pa, con
 template<bool COUNT>
 __global__ void __launch_bounds__(128) k_shadow(SceneView sv, PathArrays pa, const uint32_t *__restrict__ n_in, uint32_t *__restrict__ work,
                                                 unsigned long long *__restrict__ trav, int refill) {
-    ShadowIO io{ pa, *n_in };
+    ShadowIO io{ pa, *n_in, COUNT ? trav + 4 : nullptr };
     TraceCounters ctr{ 0, 0 };
     trace_persistent<true, COUNT>(sv, io, work, &ctr, refill);
     if (COUNT) {
@@ -577,6 +579,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
     // material sorting pays when shading diverges: on by default only for scenes with more than one material type
     const bool sorted = s.sort_by_material == 1 || (s.sort_by_material < 0 && s.n_material_types > 1);
     PathArrays pa{ wf.ray.ptr, wf.hit.ptr, wf.ps.ptr, wf.shq.ptr };
+    wf.sorted = sorted;
 
     for (auto &e : wf.events) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
     wf.events.clear();
@@ -687,8 +690,9 @@ void collect_render_stats(Scene &s) {
         (e.stage == 0 ? rs.generate_ms : e.stage == 1 ? rs.extend_ms : e.stage == 2 ? rs.shade_ms : e.stage == 3 ? rs.shadow_ms : rs.accumulate_ms) += ms;
     }
     if (s.counting) {
-        unsigned long long h[4];
+        unsigned long long h[8];
         PB2_CUDA(cudaMemcpy(h, wf.trav_counters.ptr, sizeof h, cudaMemcpyDeviceToHost));
+        rs.shadow_unoccluded = h[4];
         rs.nodes_visited = h[0] + h[2], rs.prims_tested = h[1] + h[3];
         rs.nodes_shadow = h[2], rs.prims_shadow = h[3];
     }
@@ -696,6 +700,7 @@ void collect_render_stats(Scene &s) {
     rs.extend_launches = wf.n_extend, rs.shade_launches = wf.n_shade, rs.shadow_launches = wf.n_shadow;
     rs.other_launches = (uint32_t)(wf.launches - wf.n_extend - wf.n_shade - wf.n_shadow);
     rs.shaded_paths = rs.closest_rays;
+    rs.sorted = wf.sorted ? 1u : 0u;
     s.render_stats = rs;
     wf.stats_pending = false;
 }

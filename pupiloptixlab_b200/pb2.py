@@ -63,7 +63,7 @@ class RenderStats(C.Structure):
     _fields_ = [("closest_rays", u64), ("shadow_rays", u64), ("kernel_launches", u64), ("total_ms", f32), ("generate_ms", f32),
                 ("extend_ms", f32), ("shade_ms", f32), ("shadow_ms", f32), ("accumulate_ms", f32), ("nodes_visited", u64),
                 ("prims_tested", u64), ("nodes_shadow", u64), ("prims_shadow", u64), ("batches", u32), ("rounds", u32),
-                ("extend_launches", u32), ("shade_launches", u32), ("shadow_launches", u32), ("other_launches", u32), ("shaded_paths", u64)]
+                ("extend_launches", u32), ("shade_launches", u32), ("shadow_launches", u32), ("other_launches", u32), ("shaded_paths", u64), ("shadow_unoccluded", u64), ("sorted", u32), ("pad0", u32)]
 
 
 class KatBsdf(C.Structure):  # csrc/kat.cu
