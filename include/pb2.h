@@ -160,7 +160,10 @@ int pb2_scene_set_camera(pb2_scene *scene, const float sample_to_camera[16], con
 /* replaces GAS::Create + IAS::Create (framework/world/gas_manager.cpp:69-245, ias_manager.cpp:29-114):
  * GPU build of one world-space compressed 8-wide BVH over every instance.  stats may be NULL. */
 int pb2_bvh_build(pb2_scene *scene, pb2_build_stats *stats);
-/* builder: 0 = LBVH (Morton order), 1 = binned SAH (default) */
+/* builder: 0 = LBVH over 63-bit Morton codes (default), 1 = binned-SAH sweep along the Morton order (16 equal-count bins
+ * per node, exact sweep below 17 primitives; bvh_sah.cu).  On the 30 M-triangle terrain builder 1 is measured WORSE
+ * (40 vs 24 nodes per primary ray, 85 vs 25 ms build, profiles/README.md): splits that do not fall on octree-cell
+ * boundaries of the Z-curve produce overlapping boxes.  A spatial (re-partitioning) binned SAH is not built yet. */
 int pb2_scene_set_builder(pb2_scene *scene, int builder);
 
 /* parity / benchmark hooks for the two optixTrace flavours (main.cu:80-85,161-166; emitter.h:91-100).

@@ -3,7 +3,7 @@
 // Replaces the closed-source OptiX acceleration-structure build of the reference
 // (GAS::Create framework/world/gas_manager.cpp:69-245, IAS::Create framework/world/ias_manager.cpp:29-114):
 // every instance's primitives are transformed to world space, one binary BVH is built over all of
-// them (LBVH over 63-bit Morton codes, or binned SAH — see bvh_sah.cuh) and collapsed top-down into
+// them (LBVH over 63-bit Morton codes, or binned SAH along the Morton order — bvh_sah.cu) and collapsed top-down into
 // 80-byte BVH8 nodes with quantised child boxes; primitive records are rewritten in leaf order.
 //
 // Stages (all on the scene's stream):
@@ -372,8 +372,8 @@ __global__ void k_collapse(CollapseCtx c, const uint4 *__restrict__ q_in, uint32
 
 // bvh_sah.cu: binned-SAH binary tree producing the same BinTree arrays + `sorted` permutation
 bool sah_builder_available();
-void build_binary_sah(cudaStream_t st, uint32_t n, const float4 *box_lo, const float4 *box_hi, const int *scene_bounds, int *left, int *right, int2 *range,
-                      float4 *lo, float4 *hi, uint32_t *sorted);
+void build_binary_sah(cudaStream_t st, uint32_t n, const float4 *box_lo, const float4 *box_hi, const uint32_t *sorted, int *left, int *right, int2 *range,
+                      float4 *lo, float4 *hi);
 
 void build_bvh(Scene &s) {
     cudaStream_t st = s.stream;
@@ -426,9 +426,7 @@ void build_bvh(Scene &s) {
     DevBuf<float4> nlo(n), nhi(n);
     BinTree t{ left.ptr, right.ptr, parent.ptr, range.ptr, nlo.ptr, nhi.ptr, n };
 
-    if (s.builder == 1 && n > 1 && sah_builder_available()) {
-        build_binary_sah(st, n, box_lo.ptr, box_hi.ptr, bounds.ptr, left.ptr, right.ptr, range.ptr, nlo.ptr, nhi.ptr, sorted.ptr);
-    } else {
+    {
         DevBuf<uint64_t> keys(n), keys_sorted(n);
         DevBuf<uint32_t> vals(n);
         k_morton<<<div_up(n, 256), 256, 0, st>>>(box_lo.ptr, box_hi.ptr, bounds.ptr, n, keys.ptr, vals.ptr);
@@ -437,17 +435,18 @@ void build_bvh(Scene &s) {
         PB2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.ptr, keys_sorted.ptr, vals.ptr, sorted.ptr, (int)n, 0, 63, st));
         DevBuf<uint8_t> tmp(tmp_bytes);
         PB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys.ptr, keys_sorted.ptr, vals.ptr, sorted.ptr, (int)n, 0, 63, st));
-        if (n > 1) {
+        if (n > 1 && s.builder == 1 && sah_builder_available()) {
+            // binned SAH over the Morton-ordered sequence (bvh_sah.cu); node boxes come out of the sweep
+            build_binary_sah(st, n, box_lo.ptr, box_hi.ptr, sorted.ptr, left.ptr, right.ptr, range.ptr, nlo.ptr, nhi.ptr);
+        } else if (n > 1) {
             k_radix_tree<<<div_up(n - 1, 256), 256, 0, st>>>(keys_sorted.ptr, t);
             PB2_LAUNCH_CHECK();
             DevBuf<int> arrive(n);
             arrive.zero(st);
             k_refit<<<div_up(n, 256), 256, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr);
             PB2_LAUNCH_CHECK();
-            PB2_CUDA(cudaStreamSynchronize(st)); // tmp / arrive / keys go out of scope
-        } else {
-            PB2_CUDA(cudaStreamSynchronize(st));
         }
+        PB2_CUDA(cudaStreamSynchronize(st)); // tmp / arrive / keys go out of scope
     }
 
     // ---- collapse ----
@@ -498,6 +497,7 @@ void build_bvh(Scene &s) {
     s.build_stats.build_ms = ms;
     s.build_stats.sah_cost = root_area > 0.f ? sah_host / root_area : 0.f;
     s.build_stats.max_depth = host_counters[3];
+    if (host_counters[3] > PB2_STACK_SIZE - 2) throw std::runtime_error("pb2_bvh_build: wide tree deeper than the traversal stack (" + std::to_string(host_counters[3]) + " levels)");
     s.bvh_valid = true;
 }
 }// namespace pb2

@@ -265,7 +265,7 @@ int pb2_scene_set_camera(pb2_scene *scene, const float s2c[16], const float c2w[
     PB2_CATCH
 }
 int pb2_scene_set_builder(pb2_scene *scene, int builder) {
-    if (!scene || builder < 0 || builder > 1) return fail(PB2_ERR_ARG, "pb2_scene_set_builder: 0 = LBVH, 1 = binned SAH");
+    if (!scene || builder < 0 || builder > 1) return fail(PB2_ERR_ARG, "pb2_scene_set_builder: 0 = LBVH, 1 = binned SAH along the Morton order");
     S(scene)->builder = builder;
     S(scene)->bvh_valid = false;
     return PB2_OK;

@@ -36,7 +36,7 @@ struct Scene {
     DevBuf<uint32_t> trace_work; // work counter of the persistent trace kernels
     uint32_t n_nodes = 0, n_prims = 0;
     bool bvh_valid = false;
-    int builder = 1; // 0 LBVH, 1 binned SAH
+    int builder = 0; // 0 LBVH (default: measured better on every config so far), 1 binned SAH sweep along the Morton order
     pb2_build_stats build_stats{};
 
     // options

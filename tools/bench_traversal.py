@@ -63,7 +63,7 @@ def main():
     bs = pupil.build_stats()
     builds = [bs.build_ms]
     for _ in range(2):  # rebuild twice more: steady-state build time (allocator warm)
-        pupil.set_bvh_builder(args.builder if args.builder >= 0 else 1)
+        pupil.set_bvh_builder(args.builder if args.builder >= 0 else 0)
         builds.append(pupil.build_stats().build_ms)
     scene = pupil.scene_handle()
     tri_bytes = bs.n_triangles * 230
