@@ -130,6 +130,10 @@ int pb2_device_count(void);
 /* ---- device memory (BufferManager / CudaMemcpyToDevice, framework/system/buffer.cpp:39-99, cuda/util.h:40-75) */
 int pb2_malloc(void **dptr, uint64_t bytes); /* zero-initialised, like Buffer allocation (buffer.cpp:44-45) */
 int pb2_free(void *dptr);
+/* Device blocks freed by the library (pb2_free, scene destruction, BVH rebuilds) are cached per device and reused:
+ * cudaMalloc/cudaFree of GB-sized arrays cost 0.3-0.8 s per scene reload on B200 (the reference frees and reallocates
+ * through cudaMalloc on every SetScene, system.cpp:143-165).  pb2_trim returns the cache to the driver. */
+int pb2_trim(void);
 int pb2_upload(void *dptr, const void *host, uint64_t bytes);
 int pb2_download(void *host, const void *dptr, uint64_t bytes);
 int pb2_memset(void *dptr, int value, uint64_t bytes);

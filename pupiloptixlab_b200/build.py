@@ -15,13 +15,14 @@ from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
 ROOT = PKG.parent
-BUILD = PKG / "_build"
+# PB2_BUILD_DIR / PB2_NVCC_EXTRA: side-by-side variant builds for A/B measurements (tools/, profiles/); the product uses _build
+BUILD = PKG / os.environ.get("PB2_BUILD_DIR", "_build")
 CSRC = PKG / "csrc"
 HOST = PKG / "host"
 
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v", *os.environ.get("PB2_NVCC_EXTRA", "").split()]
 CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
 
 

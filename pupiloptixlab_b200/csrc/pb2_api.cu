@@ -2,7 +2,10 @@
 // host <-> device conversion of the POD records.  No compute lives here.
 #include "scene.cuh"
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
+#include <unordered_map>
 
 namespace pb2 {
 void collect_render_stats(Scene &s); // wavefront.cu
@@ -67,6 +70,86 @@ SceneView Scene::view() const {
 }
 }// namespace pb2
 
+
+// ---- device memory pool (util.cuh) ---------------------------------------------------------------------------
+namespace pb2 {
+namespace {
+struct Pool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;  // cached blocks by size
+    std::unordered_map<void *, size_t> owned;   // every block handed out or cached -> its size
+    size_t cached = 0;
+    size_t cap = 48ull << 30;                   // cached bytes kept per device; beyond it blocks go back to the driver
+};
+Pool &pool_of_current_device() {
+    static std::mutex mu;
+    static std::map<int, std::unique_ptr<Pool>> pools;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    auto &p = pools[dev];
+    if (!p) p = std::make_unique<Pool>();
+    return *p;
+}
+size_t pool_round(size_t bytes) { return bytes <= (1u << 20) ? (bytes + 511) & ~size_t(511) : (bytes + (2u << 20) - 1) & ~size_t((2u << 20) - 1); }
+void pool_trim_locked(Pool &p) {
+    for (auto &kv : p.free_blocks) {
+        cudaFree(kv.second);
+        p.owned.erase(kv.second);
+    }
+    p.free_blocks.clear();
+    p.cached = 0;
+}
+}// namespace
+void *pool_alloc(size_t bytes) {
+    if (!bytes) return nullptr;
+    Pool &p = pool_of_current_device();
+    const size_t want = pool_round(bytes);
+    std::lock_guard<std::mutex> g(p.mu);
+    auto it = p.free_blocks.lower_bound(want);
+    if (it != p.free_blocks.end() && it->first <= want + want / 4 + (64u << 10)) { // at most 25 % (+64 KiB) of slack
+        void *ptr = it->second;
+        p.cached -= it->first;
+        p.free_blocks.erase(it);
+        return ptr;
+    }
+    void *ptr = nullptr;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e == cudaErrorMemoryAllocation) { // give the cache back and try once more
+        cudaGetLastError();
+        pool_trim_locked(p);
+        e = cudaMalloc(&ptr, want);
+    }
+    PB2_CUDA(e);
+    p.owned[ptr] = want;
+    return ptr;
+}
+void pool_free(void *ptr) noexcept {
+    if (!ptr) return;
+    cudaDeviceSynchronize(); // what cudaFree guarantees: nothing in flight still touches the block when it changes owner
+    Pool &p = pool_of_current_device();
+    std::lock_guard<std::mutex> g(p.mu);
+    auto it = p.owned.find(ptr);
+    if (it == p.owned.end()) { // not ours (allocated before a device switch): hand it straight back
+        cudaFree(ptr);
+        return;
+    }
+    if (p.cached + it->second > p.cap) {
+        cudaFree(ptr);
+        p.owned.erase(it);
+        return;
+    }
+    p.free_blocks.emplace(it->second, ptr);
+    p.cached += it->second;
+}
+void pool_trim() noexcept {
+    cudaDeviceSynchronize();
+    Pool &p = pool_of_current_device();
+    std::lock_guard<std::mutex> g(p.mu);
+    pool_trim_locked(p);
+}
+}// namespace pb2
+
 using namespace pb2;
 
 static thread_local std::string g_last_error;
@@ -124,14 +207,20 @@ int pb2_malloc(void **dptr, uint64_t bytes) {
     if (!dptr) return fail(PB2_ERR_ARG, "pb2_malloc: null");
     *dptr = nullptr;
     if (!bytes) return PB2_OK;
-    PB2_CUDA(cudaMalloc(dptr, bytes));
+    *dptr = pool_alloc(bytes);
     PB2_CUDA(cudaMemset(*dptr, 0, bytes));
     return PB2_OK;
     PB2_CATCH
 }
 int pb2_free(void *dptr) {
     PB2_TRY
-    if (dptr) PB2_CUDA(cudaFree(dptr));
+    pool_free(dptr);
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_trim(void) {
+    PB2_TRY
+    pool_trim();
     return PB2_OK;
     PB2_CATCH
 }

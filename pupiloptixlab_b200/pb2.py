@@ -6,13 +6,14 @@ initialising raises.  torch is not needed here; device buffers are plain pointer
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "_build" / "libpb2.so"
+LIB_PATH = PKG / os.environ.get("PB2_BUILD_DIR", "_build") / "libpb2.so"
 
 f32, i32, u32, u64 = C.c_float, C.c_int32, C.c_uint32, C.c_uint64
 
@@ -84,7 +85,7 @@ def lib():
         P, vp = C.POINTER, C.c_void_p
         L.pb2_last_error.restype = C.c_char_p
         sigs = {
-            "pb2_init": [C.c_int], "pb2_device_count": [], "pb2_malloc": [P(vp), u64], "pb2_free": [vp], "pb2_upload": [vp, vp, u64],
+            "pb2_init": [C.c_int], "pb2_device_count": [], "pb2_malloc": [P(vp), u64], "pb2_free": [vp], "pb2_trim": [], "pb2_upload": [vp, vp, u64],
             "pb2_download": [vp, vp, u64], "pb2_memset": [vp, C.c_int, u64], "pb2_scene_create": [P(vp)], "pb2_scene_destroy": [vp],
             "pb2_scene_clear": [vp], "pb2_scene_set_stream": [vp, vp],
             "pb2_scene_add_mesh": [vp, vp, vp, vp, vp, u32, u32, P(u32)],

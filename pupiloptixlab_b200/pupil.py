@@ -12,6 +12,7 @@ No CPU path exists: without the built libraries or without a CUDA device, init()
 """
 from __future__ import annotations
 
+import os
 import ctypes as C
 from pathlib import Path
 
@@ -20,7 +21,7 @@ import numpy as np
 from . import pb2
 from .scenes import SceneDesc, to_xml_string
 
-LIB_PATH = pb2.PKG / "_build" / "libpupil_host.so"
+LIB_PATH = pb2.PKG / os.environ.get("PB2_BUILD_DIR", "_build") / "libpupil_host.so"
 u32, i32, f32, u64 = C.c_uint32, C.c_int32, C.c_float, C.c_uint64
 _lib = None
 _mesh_serial = 0
