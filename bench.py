@@ -372,7 +372,7 @@ def main():
             "config": {"workload": w["label"] if not args.spp else f"{args.workload} {args.width}x{args.height}, {spp} spp, max depth {args.depth}",
                        "width": args.width, "height": args.height, "max_depth": args.depth, "spp_per_step": spp, "triangles": desc.num_triangles(),
                        "sharding": f"sample-index (seed = rank + i*{world}), sum buffers + NCCL reduce to rank 0" if world > 1 else "none",
-                       "l2": "path-state working set per batch (~0.6 GB) and accumulation buffers exceed the 126 MB L2; no explicit flush"},
+                       "l2": "path-state working set per batch (32 Mi paths, ~4.7 GB) and accumulation buffers exceed the 126 MB L2; no explicit flush"},
             "mrays_per_s": mrays, "rays_per_sample": (closest_all + shadow_all) / (n_px * spp * world * args.steps),
             "bvh": {"build_ms": build.build_ms, "n_prims": build.n_prims, "n_nodes": build.n_nodes, "bytes": build.bvh_bytes, "sah_cost": build.sah_cost},
             "scene_load_s": load_s, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,

@@ -566,7 +566,10 @@ void render(Scene &s, const pb2_launch_params &lp) {
 
     const uint32_t n_pixels = lp.width * lp.height;
     const uint32_t n_frames = std::max(1u, lp.n_frames);
-    const uint64_t target = s.paths_in_flight ? s.paths_in_flight : (4ull << 20);
+    // paths in flight per batch: measured on the Cornell box at 1080p (profiles/README.md) 2 Mi -> 927, 4 Mi -> 1054, 16 Mi ->
+    // 1202, 32 Mi -> 1226, 64 Mi -> 1239 Msamples/s (later bounces leave short queues; bigger batches amortise their
+    // launch gaps and tails).  32 Mi paths = 4.7 GB of path state out of 180 GB.
+    const uint64_t target = s.paths_in_flight ? s.paths_in_flight : (32ull << 20);
     const uint32_t S = (uint32_t)std::min<uint64_t>(n_frames, std::max<uint64_t>(1, target / n_pixels));
     const uint32_t rounds = std::max(1u, lp.max_depth);
     wf.ensure((uint64_t)S * n_pixels, rounds + 1);
