@@ -36,13 +36,20 @@ enum { PB2_EMIT_NONE = 0, PB2_EMIT_TRI = 1, PB2_EMIT_SPHERE = 2, PB2_EMIT_CONST_
 #define PB2_INST_FLIP_TEX 2u     /* TriMesh::flip_tex_coords, geometry.h:20 */
 #define PB2_MESH_SPHERE 0xFFFFFFFFu /* mesh id of the analytic unit sphere (centre 0, radius 1), world/render_object.cpp:30-35 */
 
-/* cuda::Texture, framework/cuda/texture.h:10-31 — RGB constant or checkerboard; r0/r1 = rows 0 and 1 of
- * the to_uv transform (the only rows Sample() reads, :34-36). */
+/* cudaTextureAddressMode / cudaTextureFilterMode values, = util::ETextureAddressMode / ETextureFilterMode
+ * (framework/util/texture.h:10-20) */
+enum { PB2_ADDR_WRAP = 0, PB2_ADDR_CLAMP = 1, PB2_ADDR_MIRROR = 2, PB2_ADDR_BORDER = 3 };
+enum { PB2_FILTER_POINT = 0, PB2_FILTER_LINEAR = 1 };
+
+/* cuda::Texture, framework/cuda/texture.h:10-31 — RGB constant, checkerboard or bitmap; r0/r1 = rows 0 and 1 of
+ * the to_uv transform (the only rows Sample() reads, :34-36).  `bitmap` is a handle from pb2_bitmap_create. */
 typedef struct pb2_texture {
     int32_t type;
     float a[3]; /* rgb | patch1 */
     float b[3]; /*       patch2 */
     float r0[4], r1[4];
+    uint32_t pad0;
+    uint64_t bitmap; /* PB2_TEX_BITMAP: cudaTextureObject_t of a float4 array, normalised coordinates */
 } pb2_texture;
 
 /* optix::material::Material after LoadMaterial (framework/render/material/optix_material.h:10-33,
@@ -72,7 +79,13 @@ typedef struct pb2_emitter {
     pb2_texture radiance; /* const env: radiance.a = color */
     float area;
     float pos[3][3], nrm[3][3], uv[3][2]; /* TriArea: world-space v0..v2 */
-    float center[3], radius;              /* Sphere */
+    float center[3], radius;              /* Sphere; EnvMap / ConstEnv: center = scene AABB centre */
+    /* EnvMapEmitter, framework/render/emitter/env.h:6-22 (radiance = the bitmap texture) */
+    float scale, normalization;
+    uint32_t map_w, map_h;
+    float to_world[9], to_local[9];       /* rows r0,r1,r2 */
+    const float *env_tables;              /* DEVICE memory (pb2_malloc): row_cdf[map_h + 1], row_weight[map_h],
+                                             col_cdf[(map_w + 1) * map_h] back to back (world/emitter.cpp:107-149) */
 } pb2_emitter;
 
 typedef struct pb2_hit {
@@ -137,6 +150,12 @@ int pb2_trim(void);
 int pb2_upload(void *dptr, const void *host, uint64_t bytes);
 int pb2_download(void *host, const void *dptr, uint64_t bytes);
 int pb2_memset(void *dptr, int value, uint64_t bytes);
+
+/* ---- bitmaps: CudaTextureManager::GetCudaTextureObject, framework/cuda/texture.cpp:60-102 ------------- */
+/* rgba: HOST float4 texels, row 0 first (file order), copied into a cudaArray; the handle is a cudaTextureObject_t
+ * with normalised coordinates, element read mode, the given address mode on both axes and filter mode. */
+int pb2_bitmap_create(const float *rgba, uint32_t width, uint32_t height, int address_mode, int filter_mode, uint64_t *handle);
+int pb2_bitmap_destroy(uint64_t handle);
 
 /* ---- scene ------------------------------------------------------------------------------------------ */
 typedef struct pb2_scene pb2_scene;

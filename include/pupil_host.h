@@ -57,6 +57,17 @@ int pupil_get_camera(float sample_to_camera[16], float camera_to_world[16], floa
 int pupil_num_instances(void);
 int pupil_get_instance(uint32_t index, float xform[16], pb2_material *material, int32_t *emitter_offset, uint32_t *flags, uint32_t *n_prims,
                        int32_t *is_sphere);
+/* bitmap textures / environment maps handed over in memory: key must start with "mem:" and is what the XML's
+ * <string name="filename"> says; rgba = width*height float4 texels, row 0 = first row of the picture (copied) */
+int pupil_register_image(const char *key, const float *rgba, uint32_t width, uint32_t height);
+/* util::BitmapTexture::Load / Save (framework/util/texture.cpp:87-174, :13-85) on their own: hdr, exr, png, pfm in;
+ * format 0 = hdr, 1 = exr, 2 = pfm out (rgba: row 0 = bottom of the picture, as in the frame buffers) */
+int pupil_image_load(const char *path, uint32_t *width, uint32_t *height, float *rgba, uint64_t capacity_in_floats);
+int pupil_image_save(const char *path, const float *rgba, uint32_t width, uint32_t height, int format);
+/* saves a named device buffer of the current scene (float4 buffers only), e.g. "final result" */
+int pupil_save_buffer(const char *name, const char *path, int format);
+/* EmitterHelper's env-map tables (world/emitter.cpp:107-149): pass NULL arrays to query the sizes */
+int pupil_get_env_tables(uint32_t *map_w, uint32_t *map_h, float *row_cdf, float *row_weight, float *col_cdf);
 int pupil_num_area_emitters(void);
 int pupil_get_emitters(pb2_emitter *areas, pb2_emitter *env, int32_t *has_env);
 /* World::GetSceneHandle(): the pb2 scene (BVH built, camera and emitters uploaded) for pb2_trace_* etc. */

@@ -103,6 +103,18 @@ int orc_add_shape(void *s, int shape_type, const orc_transform *to_world, const 
                                                nf, pos, nrm, uv, idx);
 }
 void orc_set_env_const(void *s, float r, float g, float b) { static_cast<SceneT *>(s)->set_env_const(r, g, b); }
+void orc_set_env_map(void *s, const float *rgba, uint32_t w, uint32_t h, float scale, const orc_transform *to_world) {
+    static_cast<SceneT *>(s)->set_env_map(rgba, w, h, scale, *to_world);
+}
+/* BuildEnvMapCdfTable (world/emitter.cpp:107-149) on its own: row_cdf[h + 1], row_weight[h], col_cdf[(w + 1) * h] */
+float orc_build_env_tables(const float *rgba, uint32_t w, uint32_t h, float *row_cdf, float *row_weight, float *col_cdf) {
+    EnvTables t = build_env_tables(rgba, w, h);
+    std::memcpy(row_cdf, t.row_cdf.data(), (h + 1) * sizeof(float));
+    std::memcpy(row_weight, t.row_weight.data(), h * sizeof(float));
+    std::memcpy(col_cdf, t.col_cdf.data(), (size_t)(w + 1) * h * sizeof(float));
+    return t.normalization;
+}
+float orc_texture_weight(const orc_texture *t) { return tex_max_weight(*t); } /* GetWeight, world/emitter.cpp:77-101 */
 void orc_finalize(void *s) { static_cast<SceneT *>(s)->finalize(); }
 
 void orc_get_camera(void *sp, float *s2c16, float *c2w16, float *fov_y) {

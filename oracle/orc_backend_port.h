@@ -16,6 +16,7 @@
 #define ORC_BACKEND_PORT_H
 #include "orc_types.h"
 #include "orc_vec.h"
+#include "orc_tex2d.h"
 
 namespace orc {
 
@@ -199,11 +200,15 @@ struct PortBackend {
         return normalize(ne);
     }
 
-    // ---- cuda/texture.h:33-57 (RGB + checkerboard; bitmap is not used by any config) ---------
+    // ---- cuda/texture.h:33-57 (bitmap: tex2D emulated by orc_tex2d.h) ---------------------------
     static f3 tex_sample(const orc_texture &t, f2 uv) {
         f4 tex{ uv.x, uv.y, 0.f, 1.f };
         float tex_x = dot(f4{ t.to_uv[0], t.to_uv[1], t.to_uv[2], t.to_uv[3] }, tex);
         float tex_y = dot(f4{ t.to_uv[4], t.to_uv[5], t.to_uv[6], t.to_uv[7] }, tex);
+        if (t.type == ORC_TEX_BITMAP) {
+            const Tex2dResult c = tex2d(t.bitmap, t.bitmap_w, t.bitmap_h, t.address_mode, t.filter_mode, tex_x, tex_y);
+            return mk3(c.x, c.y, c.z);
+        }
         if (t.type == ORC_TEX_CHECKERBOARD) {
             tex_x = tex_x - (tex_x > 0.f ? floorf(tex_x) : ceilf(tex_x));
             tex_y = tex_y - (tex_y > 0.f ? floorf(tex_y) : ceilf(tex_y));
@@ -499,6 +504,26 @@ struct PortBackend {
             radiance = ld3(e.radiance.a);
             position = hit_pos + wi * out.distance;
             normal = mk3(0.f); // normalize(center - pos) in the reference; never read by the integrator
+        } else if (e.type == ORC_EMIT_ENV_MAP) { // env.h:24-48
+            unsigned int row_index = 0;
+            for (; row_index < (e.map_h + 1) - 1; ++row_index) {
+                if (xi.x <= e.row_cdf[row_index]) break;
+            }
+            unsigned int col_index = 0;
+            for (int i = row_index * (e.map_w + 1); col_index < e.map_w - 1; ++i, ++col_index) {
+                if (xi.y <= e.col_cdf[i]) break;
+            }
+            const float phi = col_index * kPi * 2.f / e.map_w;
+            const float theta = row_index * kPi / e.map_h;
+            const f3 local_wi = mk3(sinf(theta) * sinf(kPi - phi), cosf(theta), sinf(theta) * cosf(kPi - phi));
+            wi = mk3(dot(ld3(e.to_world), local_wi), dot(ld3(e.to_world + 3), local_wi), dot(ld3(e.to_world + 6), local_wi));
+            out.distance = kMaxDistance;
+            const f2 tex = mk2(phi * 0.5f * kInvPi, theta * kInvPi);
+            radiance = tex_sample(e.radiance, tex) * e.scale;
+            out.pdf = luminance(radiance) * e.row_weight[row_index] * e.normalization / fmaxf(1e-4f, fabsf(sinf(theta)));
+            if (out.pdf < 0.f) out.pdf = 0.f;
+            position = hit_pos + wi * out.distance;
+            normal = mk3(0.f); // as for the constant environment
         } else {
             return;
         }
@@ -517,6 +542,17 @@ struct PortBackend {
         } else if (e.type == ORC_EMIT_CONST_ENV) { // env.h:82-85
             pdf = 0.25f * kInvPi;
             radiance = ld3(e.radiance.a);
+        } else if (e.type == ORC_EMIT_ENV_MAP) { // env.h:50-64
+            f3 dir = normalize(emit_pos - scatter_pos);
+            dir = mk3(dot(ld3(e.to_local), dir), dot(ld3(e.to_local + 3), dir), dot(ld3(e.to_local + 6), dir));
+            const float phi = kPi - atan2f(dir.x, dir.z);
+            const float theta = acosf(dir.y);
+            const f2 tex = mk2(phi * 0.5f * kInvPi, theta * kInvPi);
+            unsigned int row_index = static_cast<unsigned int>(tex.y * e.map_h);
+            row_index = row_index > e.map_h - 2u ? e.map_h - 2u : row_index; // clamp(row_index, 0u, map_size.y - 2u)
+            radiance = tex_sample(e.radiance, tex) * e.scale;
+            const float w0 = e.row_weight[row_index], w1 = e.row_weight[row_index + 1], t = tex.y * e.map_h - 1.f * row_index;
+            pdf = luminance(radiance) * (w0 + t * (w1 - w0)) * e.normalization / fmaxf(1e-4f, fabsf(sinf(theta)));
         }
     }
     static f3 emitter_radiance(const orc_emitter &e, f2 uv) { // emitter.h:54-71

@@ -114,6 +114,7 @@ struct RefBackend {
         r.transform.r1 = make_float4(t.to_uv[4], t.to_uv[5], t.to_uv[6], t.to_uv[7]);
         r.transform.r2 = make_float4(t.to_uv[8], t.to_uv[9], t.to_uv[10], t.to_uv[11]);
         r.transform.r3 = make_float4(t.to_uv[12], t.to_uv[13], t.to_uv[14], t.to_uv[15]);
+        r.bitmap = t.bitmap, r.bitmap_w = t.bitmap_w, r.bitmap_h = t.bitmap_h, r.address_mode = t.address_mode, r.filter_mode = t.filter_mode;
         return r;
     }
     static f3 tex_sample(const orc_texture &t, f2 uv) { return c(tex(t).Sample(float2{ uv.x, uv.y })); }
@@ -210,6 +211,17 @@ struct RefBackend {
         } else if (e.type == ORC_EMIT_CONST_ENV) {
             r.const_env.color = ld3(e.radiance.a);
             r.const_env.center = make_float3(0.f);
+        } else if (e.type == ORC_EMIT_ENV_MAP) { // the reference's own EnvMapEmitter over host-memory views
+            r.env_map.radiance = tex(e.radiance);
+            r.env_map.center = make_float3(0.f);
+            r.env_map.map_size = make_uint2(e.map_w, e.map_h);
+            r.env_map.row_cdf.SetData(reinterpret_cast<CUdeviceptr>(e.row_cdf), static_cast<size_t>(e.map_h) + 1);
+            r.env_map.col_cdf.SetData(reinterpret_cast<CUdeviceptr>(e.col_cdf), static_cast<size_t>(e.map_w + 1) * e.map_h);
+            r.env_map.row_weight.SetData(reinterpret_cast<CUdeviceptr>(e.row_weight), static_cast<size_t>(e.map_h));
+            r.env_map.to_world.r0 = ld3(e.to_world), r.env_map.to_world.r1 = ld3(e.to_world + 3), r.env_map.to_world.r2 = ld3(e.to_world + 6);
+            r.env_map.to_local.r0 = ld3(e.to_local), r.env_map.to_local.r1 = ld3(e.to_local + 3), r.env_map.to_local.r2 = ld3(e.to_local + 6);
+            r.env_map.normalization = e.normalization;
+            r.env_map.scale = e.scale;
         }
         return r;
     }
@@ -223,7 +235,7 @@ struct RefBackend {
         geo.position = c(hit_pos), geo.normal = c(hit_n), geo.texcoord = float2{ 0.f, 0.f };
         em.SampleDirect(rec, geo, float2{ xi.x, xi.y });
         st3(out.radiance, rec.radiance), st3(out.wi, rec.wi), st3(out.pos, rec.pos);
-        if (e.type != ORC_EMIT_CONST_ENV) st3(out.normal, rec.normal); // env normal depends on the scene centre; unused
+        if (e.type != ORC_EMIT_CONST_ENV && e.type != ORC_EMIT_ENV_MAP) st3(out.normal, rec.normal); // env normal depends on the scene centre; unused
         out.distance = rec.distance, out.pdf = rec.pdf, out.is_delta = rec.is_delta;
     }
     static void emitter_eval(const orc_emitter &e, f3 emit_pos, f3 emit_n, f2 emit_uv, f3 scatter_pos, f3 &radiance, float &pdf) {

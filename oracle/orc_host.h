@@ -220,11 +220,35 @@ inline MeshData cube_mesh() { // [-1,1]^3, 6 faces x 4 vertices, face order -X -
 // ---- textures / materials: render/material/optix_material.cpp:9-130 -----------------------------
 inline f3 tex_pixel_average(const orc_texture &t) { // :9-36
     if (t.type == ORC_TEX_CHECKERBOARD) return f3{ t.a[0] + t.b[0], t.a[1] + t.b[1], t.a[2] + t.b[2] } * 0.5f;
+    if (t.type == ORC_TEX_BITMAP) { // :19-30
+        float r = 0.f, g = 0.f, b = 0.f;
+        for (int i = 0, idx = 0; i < t.bitmap_h; ++i) {
+            for (int j = 0; j < t.bitmap_w; ++j) {
+                r += t.bitmap[idx++];
+                g += t.bitmap[idx++];
+                b += t.bitmap[idx++];
+                idx++; // a
+            }
+        }
+        const float inv = 1.0f / (1.f * t.bitmap_h * t.bitmap_w); // float3 / float, cuda/vec_math.h:425-428
+        return f3{ r, g, b } * inv;
+    }
     return f3{ t.a[0], t.a[1], t.a[2] };
 }
 inline float tex_max_weight(const orc_texture &t) { // world/emitter.cpp:73-101 (GetWeight)
     auto mx = [](float r, float g, float b) { return (r > g ? (r > b ? r : b) : (g > b ? g : b)); };
     if (t.type == ORC_TEX_CHECKERBOARD) return (mx(t.a[0], t.a[1], t.a[2]) + mx(t.b[0], t.b[1], t.b[2])) * 0.5f;
+    if (t.type == ORC_TEX_BITMAP) { // :89-99 — the reference indexes (i * w + j) with i < w, j < h (its own transposition);
+        float w = 0.f;             // DEFINED: indices past the image (w > h) are skipped instead of read
+        const size_t bw = (size_t)t.bitmap_w, bh = (size_t)t.bitmap_h;
+        for (size_t i = 0; i < bw; i++)
+            for (size_t j = 0; j < bh; j++) {
+                const size_t px = i * bw + j;
+                if (px >= bw * bh) continue;
+                w += mx(t.bitmap[px * 4 + 0], t.bitmap[px * 4 + 1], t.bitmap[px * 4 + 2]);
+            }
+        return w / (1.f * bw * bh);
+    }
     return mx(t.a[0], t.a[1], t.a[2]);
 }
 inline float lum(f3 c) { return 0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z; } // optix/util.h:161-163
@@ -357,6 +381,48 @@ inline void add_sphere_area_emitter(std::vector<orc_emitter> &out, const m44 &xf
     e.weight = tex_max_weight(radiance) * e.area;
     out.push_back(e);
 }
+// BuildEnvMapCdfTable, world/emitter.cpp:107-149.  Output layout (padded, see orc_types.h): row_cdf[h + 2],
+// row_weight[h + 1], col_cdf[(w + 1) * (h + 1)]; returns the normalization.
+struct EnvTables {
+    std::vector<float> row_cdf, row_weight, col_cdf;
+    float normalization = 0.f;
+};
+inline EnvTables build_env_tables(const float *rgba, size_t w, size_t h) {
+    EnvTables t;
+    t.col_cdf.resize((w + 1) * h);
+    t.row_cdf.resize(h + 1);
+    t.row_weight.resize(h);
+    size_t col_index = 0, row_index = 0;
+    float row_sum = 0.f;
+    t.row_cdf[row_index++] = 0.f;
+    for (auto y = 0u; y < h; ++y) {
+        float col_sum = 0.f;
+        t.col_cdf[col_index++] = 0.f;
+        for (auto x = 0u; x < w; ++x) {
+            auto pixel_index = y * w + x;
+            auto r = rgba[pixel_index * 4 + 0];
+            auto g = rgba[pixel_index * 4 + 1];
+            auto b = rgba[pixel_index * 4 + 2];
+            col_sum += lum(f3{ r, g, b });
+            t.col_cdf[col_index++] = col_sum;
+        }
+        for (auto x = 1u; x < w; ++x) t.col_cdf[col_index - x - 1] /= col_sum;
+        t.col_cdf[col_index - 1] = 1.f;
+        float weight = std::sin((y + 0.5f) * 3.14159265358979323846f / h);
+        t.row_weight[y] = weight;
+        row_sum += col_sum * weight;
+        t.row_cdf[row_index++] = row_sum;
+    }
+    for (auto y = 1u; y < h; ++y) t.row_cdf[row_index - y - 1] /= row_sum;
+    t.row_cdf[row_index - 1] = 1.f;
+    t.normalization = 1.f / (row_sum * (2.f * 3.14159265358979323846f / w) * (3.14159265358979323846f / h));
+    // pad: one more row so that row_index == h (reachable in the reference, which then reads out of bounds) is defined
+    t.row_cdf.push_back(1.f);
+    t.row_weight.push_back(t.row_weight[h - 1]);
+    t.col_cdf.insert(t.col_cdf.end(), t.col_cdf.end() - (w + 1), t.col_cdf.end());
+    return t;
+}
+
 inline void compute_select_probability(std::vector<orc_emitter> &areas, orc_emitter *env) { // :321-337
     float area_weight_sum = 0.f;
     for (auto &e : areas) area_weight_sum += e.weight;

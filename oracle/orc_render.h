@@ -67,6 +67,8 @@ struct Scene {
     std::vector<orc_emitter> areas;
     bool has_env = false;
     orc_emitter env{};
+    EnvTables env_tables;          // owns the tables env.row_cdf / row_weight / col_cdf point at
+    std::vector<float> env_bitmap; // owns the texels env.radiance.bitmap points at
     std::vector<WorldTri> tris;
     std::vector<WorldSphere> spheres;
     std::vector<BvhNode> bvh;
@@ -132,6 +134,27 @@ struct Scene {
         env.type = ORC_EMIT_CONST_ENV;
         env.radiance.a[0] = r, env.radiance.a[1] = g, env.radiance.a[2] = b;
         env.weight = 1.f;
+        finalized = false;
+    }
+
+    void set_env_map(const float *rgba, uint32_t w, uint32_t h, float scale, const orc_transform &xf) { // emitter.cpp:293-312, scene.cpp:207-219
+        has_env = true;
+        env = orc_emitter{};
+        env.type = ORC_EMIT_ENV_MAP;
+        env_bitmap.assign(rgba, rgba + (size_t)w * h * 4);
+        env.radiance.type = ORC_TEX_BITMAP;
+        env.radiance.bitmap = env_bitmap.data(), env.radiance.bitmap_w = (int)w, env.radiance.bitmap_h = (int)h;
+        env.radiance.address_mode = 0 /* Wrap */, env.radiance.filter_mode = 1 /* Linear */;
+        for (int i = 0; i < 16; ++i) env.radiance.to_uv[i] = (i % 5 == 0) ? 1.f : 0.f;
+        env.scale = scale;
+        env.weight = 1.f;
+        const m44 m = resolve_transform(xf), inv = inverse44(m);
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) env.to_world[r * 3 + c] = m.e[r * 4 + c], env.to_local[r * 3 + c] = inv.e[r * 4 + c];
+        env_tables = build_env_tables(env_bitmap.data(), w, h);
+        env.normalization = env_tables.normalization;
+        env.map_w = w, env.map_h = h;
+        env.row_cdf = env_tables.row_cdf.data(), env.row_weight = env_tables.row_weight.data(), env.col_cdf = env_tables.col_cdf.data();
         finalized = false;
     }
 

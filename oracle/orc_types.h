@@ -34,13 +34,16 @@ enum { ORC_EMIT_NONE = 0, ORC_EMIT_TRI = 1, ORC_EMIT_SPHERE = 2, ORC_EMIT_CONST_
 enum { ORC_SHAPE_OBJ = 1, ORC_SHAPE_SPHERE = 2, ORC_SHAPE_CUBE = 3, ORC_SHAPE_RECTANGLE = 4 }; /* resource/shape.h:28-31 */
 enum { ORC_XF_IDENTITY = 0, ORC_XF_MATRIX16 = 1, ORC_XF_MATRIX9 = 2, ORC_XF_LOOKAT = 3, ORC_XF_SRT = 4 };
 
-/* util::Texture restricted to what configs C1..C5 use (RGB / checkerboard); `to_uv` is the full
- * row-major 4x4 of util::Transform (only rows 0,1 are read on the device, cuda/texture.h:34-36). */
+/* util::Texture (framework/util/texture.h:27-65); `to_uv` is the full row-major 4x4 of util::Transform (only rows
+ * 0,1 are read on the device, cuda/texture.h:34-36).  A bitmap is float4 texels, row 0 first, borrowed from the
+ * caller; address_mode / filter_mode = util::ETextureAddressMode / ETextureFilterMode (texture.h:10-20). */
 typedef struct orc_texture {
     int32_t type;
     float a[3]; /* rgb  | checkerboard patch1 (= xml color0, resource/scene.cpp:170-172) */
     float b[3]; /*        checkerboard patch2 (= xml color1) */
     float to_uv[16];
+    int32_t bitmap_w, bitmap_h, address_mode, filter_mode;
+    const float *bitmap;
 } orc_texture;
 
 /* resource::Material (framework/resource/material.h:16-83) flattened: one struct, all slots. */
@@ -79,7 +82,7 @@ typedef struct orc_bsdf_result {
     uint32_t rng_after;
 } orc_bsdf_result;
 
-/* optix::Emitter (framework/render/emitter.h:13-23) for the three kinds the configs use */
+/* optix::Emitter (framework/render/emitter.h:13-23): tri area, sphere, constant env, env map */
 typedef struct orc_emitter {
     int32_t type;
     float weight, select_probability;
@@ -87,6 +90,13 @@ typedef struct orc_emitter {
     float area;
     float pos[3][3], nrm[3][3], uv[3][2]; /* TriArea v0..v2 (world space) */
     float center[3], radius;              /* Sphere */
+    /* EnvMapEmitter (framework/render/emitter/env.h:6-22); tables borrowed from the owner (orc scene / caller):
+     * row_cdf[map_h + 1 (+1 pad)], row_weight[map_h (+1 pad)], col_cdf[(map_w + 1) * (map_h (+1 pad row))] — the pad
+     * entries repeat the last row: the reference reads one row past its tables when xi.x > row_cdf[map_h - 1]. */
+    float scale, normalization;
+    uint32_t map_w, map_h;
+    float to_world[9], to_local[9];
+    const float *row_cdf, *row_weight, *col_cdf;
 } orc_emitter;
 
 typedef struct orc_emit_sample {

@@ -71,7 +71,7 @@ def build_host(force: bool = False) -> Path:
     hdrs = sorted(HOST.glob("*.h")) + sorted((ROOT / "include").glob("*.h"))
     common = [CXX, "-O2", "-std=c++20", "-fPIC", "-pthread", "-Wall", "-Wno-unused-function", f"-I{ROOT / 'include'}", f"-I{HOST}"]
     if force or _newer(out, [*lib_srcs, *hdrs]):
-        _run([*common, "-shared", *map(str, lib_srcs), "-o", str(out), f"-L{BUILD}", "-lpb2", "-Wl,-rpath,$ORIGIN"])
+        _run([*common, "-shared", *map(str, lib_srcs), "-o", str(out), f"-L{BUILD}", "-lpb2", "-lz", "-Wl,-rpath,$ORIGIN"])
     if force or _newer(exe, [HOST / "main.cpp", out, *hdrs]):
         _run([*common, str(HOST / "main.cpp"), "-o", str(exe), f"-L{BUILD}", "-lpupil_host", "-lpb2", "-Wl,-rpath,$ORIGIN"])
     return out

@@ -16,6 +16,11 @@ DevTexture to_dev(const pb2_texture &t) {
     memcpy(&type_bits, &t.type, 4);
     d.hdr = make_float4(type_bits, t.a[0], t.a[1], t.a[2]);
     d.b = make_float4(t.b[0], t.b[1], t.b[2], 0.f);
+    if (t.type == PB2_TEX_BITMAP) { // hdr.y / hdr.z carry the 64-bit texture object
+        const uint32_t lo = (uint32_t)(t.bitmap & 0xffffffffull), hi = (uint32_t)(t.bitmap >> 32);
+        memcpy(&d.hdr.y, &lo, 4), memcpy(&d.hdr.z, &hi, 4);
+        d.hdr.w = 0.f;
+    }
     d.r0 = make_float4(t.r0[0], t.r0[1], t.r0[2], t.r0[3]);
     d.r1 = make_float4(t.r1[0], t.r1[1], t.r1[2], t.r1[3]);
     return d;
@@ -38,6 +43,19 @@ DevEmitter to_dev(const pb2_emitter &e) {
     d.n1 = make_float4(e.nrm[1][0], e.nrm[1][1], e.nrm[1][2], e.uv[2][0]);
     d.n2 = make_float4(e.nrm[2][0], e.nrm[2][1], e.nrm[2][2], e.uv[2][1]);
     d.center_r = make_float4(e.center[0], e.center[1], e.center[2], e.radius);
+    if (e.type == PB2_EMIT_ENV_MAP) { // env.h:6-22: p* = to_world rows, n* = to_local rows, the spare w lanes carry the rest
+        float wb, hb, plo, phi;
+        const uint64_t tp = reinterpret_cast<uint64_t>(e.env_tables);
+        const uint32_t lo = (uint32_t)(tp & 0xffffffffull), hi = (uint32_t)(tp >> 32);
+        memcpy(&wb, &e.map_w, 4), memcpy(&hb, &e.map_h, 4), memcpy(&plo, &lo, 4), memcpy(&phi, &hi, 4);
+        d.area = e.normalization;
+        d.p0 = make_float4(e.to_world[0], e.to_world[1], e.to_world[2], e.scale);
+        d.p1 = make_float4(e.to_world[3], e.to_world[4], e.to_world[5], wb);
+        d.p2 = make_float4(e.to_world[6], e.to_world[7], e.to_world[8], hb);
+        d.n0 = make_float4(e.to_local[0], e.to_local[1], e.to_local[2], plo);
+        d.n1 = make_float4(e.to_local[3], e.to_local[4], e.to_local[5], phi);
+        d.n2 = make_float4(e.to_local[6], e.to_local[7], e.to_local[8], 0.f);
+    }
     return d;
 }
 
@@ -239,6 +257,58 @@ int pb2_download(void *host, const void *dptr, uint64_t bytes) {
 int pb2_memset(void *dptr, int value, uint64_t bytes) {
     PB2_TRY
     if (bytes) PB2_CUDA(cudaMemset(dptr, value, bytes));
+    return PB2_OK;
+    PB2_CATCH
+}
+
+// CudaTextureManager::GetCudaTextureObject, framework/cuda/texture.cpp:60-102
+namespace {
+std::mutex g_bitmap_mu;
+std::unordered_map<uint64_t, cudaArray_t> g_bitmaps; // texture object -> its array
+}
+int pb2_bitmap_create(const float *rgba, uint32_t width, uint32_t height, int address_mode, int filter_mode, uint64_t *handle) {
+    PB2_TRY
+    if (!rgba || !width || !height || !handle) return fail(PB2_ERR_ARG, "pb2_bitmap_create: null / empty image");
+    if (address_mode < 0 || address_mode > 3 || filter_mode < 0 || filter_mode > 1) return fail(PB2_ERR_ARG, "pb2_bitmap_create: bad address / filter mode");
+    cudaChannelFormatDesc desc = cudaCreateChannelDesc<float4>();
+    cudaArray_t arr = nullptr;
+    PB2_CUDA(cudaMallocArray(&arr, &desc, width, height));
+    const size_t pitch = (size_t)width * 4 * sizeof(float);
+    PB2_CUDA(cudaMemcpy2DToArray(arr, 0, 0, rgba, pitch, pitch, height, cudaMemcpyHostToDevice));
+    cudaResourceDesc res{};
+    res.resType = cudaResourceTypeArray;
+    res.res.array.array = arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = (cudaTextureAddressMode)address_mode;
+    td.filterMode = (cudaTextureFilterMode)filter_mode;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    td.maxAnisotropy = 1;
+    td.maxMipmapLevelClamp = 99, td.minMipmapLevelClamp = 0;
+    td.mipmapFilterMode = cudaFilterModePoint;
+    td.borderColor[0] = 1.0f;
+    td.sRGB = 0;
+    cudaTextureObject_t tex = 0;
+    cudaError_t e = cudaCreateTextureObject(&tex, &res, &td, nullptr);
+    if (e != cudaSuccess) {
+        cudaFreeArray(arr);
+        PB2_CUDA(e);
+    }
+    std::lock_guard<std::mutex> g(g_bitmap_mu);
+    g_bitmaps[(uint64_t)tex] = arr;
+    *handle = (uint64_t)tex;
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_bitmap_destroy(uint64_t handle) {
+    PB2_TRY
+    std::lock_guard<std::mutex> g(g_bitmap_mu);
+    auto it = g_bitmaps.find(handle);
+    if (it == g_bitmaps.end()) return fail(PB2_ERR_ARG, "pb2_bitmap_destroy: unknown handle");
+    cudaDeviceSynchronize();
+    cudaDestroyTextureObject((cudaTextureObject_t)handle);
+    cudaFreeArray(it->second);
+    g_bitmaps.erase(it);
     return PB2_OK;
     PB2_CATCH
 }

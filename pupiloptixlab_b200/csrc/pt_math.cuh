@@ -178,11 +178,17 @@ PB2_D float3 ggx_sample(float3 wo, float alpha, float2 xi) { // :39-57
 // ---- cuda/texture.h:33-57 -----------------------------------------------------------------------------
 PB2_D float3 tex_sample(const DevTexture *t, float2 uv) {
     const float4 hdr = __ldg(&t->hdr);
-    if (__float_as_int(hdr.x) != PB2_TEX_CHECKERBOARD) return mk3(hdr.y, hdr.z, hdr.w);
-    const float4 b = __ldg(&t->b), r0 = __ldg(&t->r0), r1 = __ldg(&t->r1);
+    if (__float_as_int(hdr.x) == PB2_TEX_RGB) return mk3(hdr.y, hdr.z, hdr.w);
+    const float4 r0 = __ldg(&t->r0), r1 = __ldg(&t->r1);
     const float4 tex = make_float4(uv.x, uv.y, 0.f, 1.f);
     float tex_x = dot(r0, tex);
     float tex_y = dot(r1, tex);
+    if (__float_as_int(hdr.x) == PB2_TEX_BITMAP) { // :52-54, the texture unit filters and wraps
+        const cudaTextureObject_t obj = (unsigned long long)__float_as_uint(hdr.y) | ((unsigned long long)__float_as_uint(hdr.z) << 32);
+        const float4 c = tex2D<float4>(obj, tex_x, tex_y);
+        return mk3(c.x, c.y, c.z);
+    }
+    const float4 b = __ldg(&t->b);
     tex_x = tex_x - (tex_x > 0.f ? floorf(tex_x) : ceilf(tex_x));
     tex_y = tex_y - (tex_y > 0.f ? floorf(tex_y) : ceilf(tex_y));
     if (tex_x < 0.f) tex_x += 1.f;
@@ -441,6 +447,31 @@ PB2_D void bsdf_eval(const LocalBsdf &b, BsdfRec &r) {
 }
 
 // ---- emitters ------------------------------------------------------------------------------------------
+// EnvMapEmitter fields as packed into DevEmitter by pb2_api.cu (to_dev)
+struct EnvMapView {
+    float3 to_world0, to_world1, to_world2, to_local0, to_local1, to_local2;
+    float scale, normalization;
+    uint32_t w, h;
+    const float *row_cdf, *row_weight, *col_cdf;
+    PB2_D explicit EnvMapView(const DevEmitter *e) {
+        const float4 p0 = __ldg(&e->p0), p1 = __ldg(&e->p1), p2 = __ldg(&e->p2), n0 = __ldg(&e->n0), n1 = __ldg(&e->n1), n2 = __ldg(&e->n2);
+        to_world0 = mk3(p0), to_world1 = mk3(p1), to_world2 = mk3(p2), to_local0 = mk3(n0), to_local1 = mk3(n1), to_local2 = mk3(n2);
+        scale = p0.w, w = __float_as_uint(p1.w), h = __float_as_uint(p2.w);
+        normalization = __ldg(&e->area);
+        const float *tables = reinterpret_cast<const float *>((unsigned long long)__float_as_uint(n0.w) | ((unsigned long long)__float_as_uint(n1.w) << 32));
+        row_cdf = tables, row_weight = tables + (h + 1u), col_cdf = tables + (2u * h + 1u);
+    }
+};
+// smallest i in [0, n) with x <= cdf[i]; n when there is none (cdf non-decreasing)
+PB2_D uint32_t first_not_less(const float *cdf, uint32_t n, float x) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (x <= __ldg(cdf + mid)) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
 struct EmitSample { // EmitterSampleRecord, render/emitter/types.h:17-26
     float3 radiance, wi;
     float distance, pdf;
@@ -486,6 +517,22 @@ PB2_D void emitter_sample_direct(const DevEmitter *e, float3 hit_pos, float3 hit
         out.distance = kMaxDistance;
         const float4 hdr = __ldg(&e->radiance.hdr);
         out.radiance = mk3(hdr.y, hdr.z, hdr.w);
+    } else if (type == PB2_EMIT_ENV_MAP) { // EnvMapEmitter::SampleDirect, env.h:24-48
+        const EnvMapView em(e);
+        // "first index whose cdf value is >= xi" over the same index ranges as the reference's linear scans (:25-31);
+        // the tables are non-decreasing, so a binary search returns the same index
+        const uint32_t row_index = first_not_less(em.row_cdf, em.h, xi.x); // candidates 0..h-1, h when none
+        const uint32_t row_t = min(row_index, em.h - 1u);                  // the reference reads past its tables for row_index == h
+        const uint32_t col_index = first_not_less(em.col_cdf + (size_t)row_t * (em.w + 1u), em.w - 1u, xi.y);
+        const float phi = col_index * kPi * 2.f / em.w;
+        const float theta = row_index * kPi / em.h;
+        const float3 local_wi = mk3(sinf(theta) * sinf(kPi - phi), cosf(theta), sinf(theta) * cosf(kPi - phi));
+        out.wi = mk3(dot(em.to_world0, local_wi), dot(em.to_world1, local_wi), dot(em.to_world2, local_wi));
+        out.distance = kMaxDistance;
+        const float2 tex = make_float2(phi * 0.5f * kInvPi, theta * kInvPi);
+        out.radiance = tex_sample(&e->radiance, tex) * em.scale;
+        out.pdf = luminance(out.radiance) * __ldg(em.row_weight + row_t) * em.normalization / fmaxf(1e-4f, fabsf(sinf(theta)));
+        if (out.pdf < 0.f) out.pdf = 0.f;
     }
 }
 // Emitter::Eval: area.h:37-45, sphere.h:34-42, env.h:82-85
@@ -504,6 +551,18 @@ PB2_D void emitter_eval(const DevEmitter *e, float3 emit_pos, float3 emit_n, flo
         pdf = 0.25f * kInvPi;
         const float4 hdr = __ldg(&e->radiance.hdr);
         radiance = mk3(hdr.y, hdr.z, hdr.w);
+    } else if (h.x == PB2_EMIT_ENV_MAP) { // EnvMapEmitter::Eval, env.h:50-64
+        const EnvMapView em(e);
+        float3 dir = normalize(emit_pos - scatter_pos);
+        dir = mk3(dot(em.to_local0, dir), dot(em.to_local1, dir), dot(em.to_local2, dir));
+        const float phi = kPi - atan2f(dir.x, dir.z);
+        const float theta = acosf(dir.y);
+        const float2 tex = make_float2(phi * 0.5f * kInvPi, theta * kInvPi);
+        uint32_t row_index = static_cast<uint32_t>(tex.y * em.h);
+        row_index = min(max(row_index, 0u), em.h - 2u);
+        radiance = tex_sample(&e->radiance, tex) * em.scale;
+        const float w0 = __ldg(em.row_weight + row_index), w1 = __ldg(em.row_weight + row_index + 1);
+        pdf = luminance(radiance) * lerp1(w0, w1, tex.y * em.h - 1.f * row_index) * em.normalization / fmaxf(1e-4f, fabsf(sinf(theta)));
     }
 }
 // Emitter::GetRadiance, render/emitter.h:54-71
@@ -512,7 +571,7 @@ PB2_D float3 emitter_radiance(const DevEmitter *e, float2 uv) {
         const float4 hdr = __ldg(&e->radiance.hdr);
         return mk3(hdr.y, hdr.z, hdr.w);
     }
-    return tex_sample(&e->radiance, uv);
+    return tex_sample(&e->radiance, uv); // area, sphere and env map alike (emitter.h:54-71: no `scale` for the env map)
 }
 // EmitterGroup::SelectOneEmiiter, render/emitter.h:110-136: linear scan over the cumulative selection
 // probability in emitter order (same selection as the reference, same fp32 running sum).

@@ -46,6 +46,7 @@ PB2_HD float3 normalize(float3 v) {
     return v * inv_len;
 }
 PB2_HD float3 lerp3(float3 a, float3 b, float t) { return a + t * (b - a); }
+PB2_HD float lerp1(float a, float b, float t) { return a + t * (b - a); } // optix::Lerp, framework/optix/util.h:181-183
 PB2_HD float3 fmin3(float3 a, float3 b) { return mk3(fminf(a.x, b.x), fminf(a.y, b.y), fminf(a.z, b.z)); }
 PB2_HD float3 fmax3(float3 a, float3 b) { return mk3(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z)); }
 

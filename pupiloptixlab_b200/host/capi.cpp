@@ -1,5 +1,6 @@
 // extern "C" veneer over the C++ host surface (include/pupil_host.h).  No logic of its own.
 #include "../../include/pupil_host.h"
+#include "image.h"
 #include "pt_pass.h"
 
 #include <cstring>
@@ -73,6 +74,47 @@ int pupil_parse_scene_xml_string(const char *xml, const char *root_dir) {
 int pupil_register_mesh(const char *key, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t nv, uint32_t nf) {
     if (!key || std::strncmp(key, "mem:", 4) != 0) return Fail("mesh keys must start with \"mem:\"");
     if (!util::Singleton<resource::ShapeManager>::instance()->LoadMeshShape(key, pos, nrm, uv, idx, nv, nf)) return Fail("empty mesh");
+    return 0;
+}
+int pupil_register_image(const char *key, const float *rgba, uint32_t width, uint32_t height) {
+    if (!key || std::strncmp(key, "mem:", 4) != 0) return Fail("image keys must start with \"mem:\"");
+    optix::material::ClearDeviceBitmaps(); // a replaced image may reuse the address a cached texture object was made from
+    if (!util::Singleton<resource::TextureManager>::instance()->RegisterImage(key, rgba, width, height)) return Fail("empty image");
+    return 0;
+}
+int pupil_image_load(const char *path, uint32_t *width, uint32_t *height, float *rgba, uint64_t capacity_in_floats) {
+    util::Image img;
+    if (!path || !util::LoadImage(path, img)) return Fail(std::string("cannot load image: ") + (path ? path : "(null)"));
+    if (width) *width = static_cast<uint32_t>(img.w);
+    if (height) *height = static_cast<uint32_t>(img.h);
+    if (rgba) {
+        if (capacity_in_floats < img.rgba.size()) return Fail("pupil_image_load: buffer too small");
+        std::memcpy(rgba, img.rgba.data(), img.rgba.size() * sizeof(float));
+    }
+    return 0;
+}
+int pupil_image_save(const char *path, const float *rgba, uint32_t width, uint32_t height, int format) {
+    if (!path || format < 0 || format > 2) return Fail("pupil_image_save: bad arguments");
+    return util::SaveImage(rgba, width, height, path, static_cast<util::EImageFileFormat>(format)) ? 0 : Fail("image saving failed");
+}
+int pupil_save_buffer(const char *name, const char *path, int format) {
+    if (!Ready() || !name || !path || format < 0 || format > 2) return Fail("pupil_save_buffer: bad arguments / no scene");
+    Buffer *b = util::Singleton<BufferManager>::instance()->GetBuffer(name);
+    if (!b || !b->cuda_ptr || b->desc.stride_in_byte != 16) return Fail("pupil_save_buffer: no such float4 buffer");
+    std::vector<float> host(static_cast<size_t>(b->desc.width) * b->desc.height * 4);
+    if (pb2_download(host.data(), b->cuda_ptr, host.size() * sizeof(float)) != PB2_OK) return Fail(pb2_last_error());
+    return util::SaveImage(host.data(), b->desc.width, b->desc.height, path, static_cast<util::EImageFileFormat>(format)) ? 0 : Fail("image saving failed");
+}
+int pupil_get_env_tables(uint32_t *map_w, uint32_t *map_h, float *row_cdf, float *row_weight, float *col_cdf) {
+    if (!HasWorld()) return Fail("no scene");
+    const pb2_emitter *e = W()->emitters->GetEnvEmitter();
+    if (!e || e->type != PB2_EMIT_ENV_MAP) return Fail("the scene has no env-map emitter");
+    if (map_w) *map_w = e->map_w;
+    if (map_h) *map_h = e->map_h;
+    auto copy = [](float *dst, const std::vector<float> &src) {
+        if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(float));
+    };
+    copy(row_cdf, W()->emitters->GetEnvRowCdf()), copy(row_weight, W()->emitters->GetEnvRowWeight()), copy(col_cdf, W()->emitters->GetEnvColCdf());
     return 0;
 }
 int pupil_clear_shapes(void) {

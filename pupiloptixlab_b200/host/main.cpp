@@ -1,30 +1,25 @@
 // path_tracer — headless counterpart of example/path_tracer/main.cpp:5-22:
 //   System::Init -> AddPass(PTPass) -> SetScene(xml) -> Run -> Destroy
 // plus what a window-less run needs: an spp limit and an image file.
-//   path_tracer --scene file.xml [--spp 64] [--depth N] [--device 0] [--out image.pfm] [--batch 16] [--builder 0|1]
+//   path_tracer --scene file.xml [--spp 64] [--depth N] [--device 0] [--out image.pfm|.exr|.hdr] [--batch 16] [--builder 0|1]
 #include "pt_pass.h"
 
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include "image.h"
+#include <filesystem>
 #include <memory>
 #include <vector>
 
 using namespace Pupil;
 
-// Portable FloatMap, RGB, little endian.  PFM stores the BOTTOM row first — the buffers' native order (row 0 =
-// bottom, as in the reference's screenshot path util/texture.cpp:37).
-static bool WritePfm(const char *path, const std::vector<float> &rgba, uint32_t w, uint32_t h) {
-    std::ofstream f(path, std::ios::binary);
-    if (!f) return false;
-    f << "PF\n" << w << " " << h << "\n-1.0\n";
-    std::vector<float> row(w * 3);
-    for (uint32_t y = 0; y < h; ++y) {
-        for (uint32_t x = 0; x < w; ++x)
-            for (int c = 0; c < 3; ++c) row[x * 3 + c] = rgba[(static_cast<size_t>(y) * w + x) * 4 + c];
-        f.write(reinterpret_cast<const char *>(row.data()), row.size() * sizeof(float));
-    }
-    return static_cast<bool>(f);
+// The reference's screenshot path (util::BitmapTexture::Save, util/texture.cpp:13-85: hdr or exr) plus PFM; the format
+// follows the file extension.
+static bool WriteImage(const char *path, const std::vector<float> &rgba, uint32_t w, uint32_t h) {
+    const std::string ext = std::filesystem::path(path).extension().string();
+    const util::EImageFileFormat fmt = ext == ".exr" ? util::EImageFileFormat::EXR : ext == ".hdr" ? util::EImageFileFormat::HDR : util::EImageFileFormat::PFM;
+    return util::SaveImage(rgba.data(), w, h, path, fmt);
 }
 
 int main(int argc, char **argv) {
@@ -42,7 +37,7 @@ int main(int argc, char **argv) {
         else if (!std::strcmp(argv[i], "--builder")) builder = std::atoi(next());
         else if (!std::strcmp(argv[i], "--verbose")) Log::level = 2;
         else {
-            std::fprintf(stderr, "usage: %s --scene file.xml [--spp N] [--depth N] [--device D] [--out image.pfm] [--batch N] [--builder 0|1]\n", argv[0]);
+            std::fprintf(stderr, "usage: %s --scene file.xml [--spp N] [--depth N] [--device D] [--out image.pfm|.exr|.hdr] [--batch N] [--builder 0|1]\n", argv[0]);
             return 2;
         }
     }
@@ -84,7 +79,7 @@ int main(int argc, char **argv) {
             std::printf("%ux%u, %u spp, depth %u: %.1f ms (%.2f Msamples/s); BVH: %llu prims, %llu nodes, %.2f ms\n", w, h, spp, lp.config.max_depth,
                         timer.ElapsedMilliseconds(), 1e-3 * w * h * spp / timer.ElapsedMilliseconds(), (unsigned long long)bs.n_prims,
                         (unsigned long long)bs.n_nodes, bs.build_ms);
-            if (!WritePfm(out_path, img, w, h)) std::fprintf(stderr, "path_tracer: cannot write %s\n", out_path), rc = 1;
+            if (!WriteImage(out_path, img, w, h)) std::fprintf(stderr, "path_tracer: cannot write %s\n", out_path), rc = 1;
         }
         system->RemovePass(pt_pass.get());
     }

@@ -1,4 +1,5 @@
 #include "resource.h"
+#include "image.h"
 
 #include <charconv>
 #include <cstring>
@@ -539,6 +540,44 @@ bool Scene::LoadFromXMLString(std::string_view text, std::filesystem::path root)
     return LoadFromRoot(parser.LoadFromString(text));
 }
 
+namespace {
+// "mem:KEY" names an image registered through TextureManager::RegisterImage; anything else is a path below the scene
+std::string ResolveImagePath(const std::filesystem::path &root, const std::string &value) {
+    if (value.rfind("mem:", 0) == 0) return value;
+    return (root / value).make_preferred().string();
+}
+}// namespace
+
+// ---- resource/texture.cpp: image cache ------------------------------------------------------------------------------
+util::Texture TextureManager::GetTexture(std::string_view path) noexcept {
+    const std::string key(path);
+    auto it = m_images.find(key);
+    if (it == m_images.end()) {
+        util::Image image;
+        if (key.rfind("mem:", 0) == 0 || !util::LoadImage(key, image)) {
+            if (key.rfind("mem:", 0) == 0) Log::Warn("image [%s] was not registered", key.c_str());
+            util::Texture grey; // the reference would hand a null bitmap to the device here
+            grey.type = util::ETextureType::RGB, grey.rgb = util::Float3{ 0.5f };
+            return grey;
+        }
+        auto data = std::make_unique<ImageData>();
+        data->w = image.w, data->h = image.h, data->rgba = std::move(image.rgba);
+        it = m_images.emplace(key, std::move(data)).first;
+    }
+    util::Texture t;
+    t.type = util::ETextureType::Bitmap;
+    t.bitmap.data = it->second->rgba.data(), t.bitmap.w = it->second->w, t.bitmap.h = it->second->h;
+    return t;
+}
+bool TextureManager::RegisterImage(std::string_view key, const float *rgba, size_t w, size_t h) noexcept {
+    if (!rgba || !w || !h) return false;
+    auto data = std::make_unique<ImageData>();
+    data->w = w, data->h = h, data->rgba.assign(rgba, rgba + w * h * 4);
+    m_images[std::string(key)] = std::move(data);
+    return true;
+}
+void TextureManager::Clear() noexcept { m_images.clear(); }
+
 void Scene::LoadXmlObj(const xml::Object *o, void *dst) noexcept {
     if (o == nullptr || dst == nullptr) return;
     switch (o->tag) {
@@ -584,9 +623,14 @@ void Scene::LoadXmlObj(const xml::Object *o, void *dst) noexcept {
                 tex->type = util::ETextureType::Checkerboard;
                 xml::LoadFloat3(o, "color0", tex->patch1, { 0.4f });
                 xml::LoadFloat3(o, "color1", tex->patch2, { 0.2f });
-            } else if (o->type == "bitmap") {
-                Log::Warn("bitmap texture [%s]: image IO is not built (SURVEY.md 8f rank 2); using mid grey", o->GetProperty("filename").c_str());
-                tex->type = util::ETextureType::RGB, tex->rgb = util::Float3{ 0.5f };
+            } else if (o->type == "bitmap") { // scene.cpp:144-166
+                const std::string value = o->GetProperty("filename");
+                *tex = util::Singleton<TextureManager>::instance()->GetTexture(ResolveImagePath(scene_root_path, value));
+                tex->bitmap.filter_mode = o->GetProperty("filter_type") == "bilinear" ? util::ETextureFilterMode::Linear : util::ETextureFilterMode::Point;
+                const std::string wrap = o->GetProperty("wrap_mode");
+                tex->bitmap.address_mode = wrap == "mirror" ? util::ETextureAddressMode::Mirror
+                                           : wrap == "clamp" ? util::ETextureAddressMode::Clamp
+                                                             : util::ETextureAddressMode::Wrap; // "repeat" and the default
             } else {
                 Log::Warn("unknown texture type [%s]", o->type.c_str());
             }
@@ -605,9 +649,18 @@ void Scene::LoadXmlObj(const xml::Object *o, void *dst) noexcept {
             } else if (o->type == "constant") {
                 e->type = EEmitterType::ConstEnv;
                 xml::LoadFloat3(o, "radiance", e->color);
-            } else if (o->type == "envmap") {
-                Log::Warn("envmap emitter [%s]: image IO is not built (SURVEY.md 8f rank 2); emitter ignored", o->GetProperty("filename").c_str());
-                e->type = EEmitterType::Unknown;
+            } else if (o->type == "envmap") { // scene.cpp:207-219
+                e->type = EEmitterType::EnvMap;
+                xml::LoadFloat(o, "scale", e->scale, 1.f);
+                e->radiance = util::Singleton<TextureManager>::instance()->GetTexture(ResolveImagePath(scene_root_path, o->GetProperty("filename")));
+                if (e->radiance.type != util::ETextureType::Bitmap) {
+                    Log::Warn("envmap emitter: no image, emitter ignored");
+                    e->type = EEmitterType::Unknown;
+                }
+                e->radiance.bitmap.filter_mode = util::ETextureFilterMode::Linear;
+                e->radiance.bitmap.address_mode = util::ETextureAddressMode::Wrap;
+                e->transform = util::Transform{};
+                LoadXmlObj(o->GetUniqueSubObject("transform"), &e->transform);
             } else {
                 Log::Warn("unknown emitter type [%s]", o->type.c_str());
             }

@@ -8,7 +8,7 @@
 //   Scene::{LoadFromXML, LoadXmlObj}                     framework/resource/scene.{h,cpp}
 //   typed property readers                               framework/resource/xml/util_loader.cpp
 //
-// Out of scope here (SURVEY.md §8f rank 2 / out): bitmap + env-map image IO, hair.  They are parsed,
+// Out of scope here: hair.  It is parsed,
 // warned about and replaced by neutral defaults so a scene still loads.
 #pragma once
 #include "util.h"
@@ -17,6 +17,7 @@
 #include <filesystem>
 #include <memory>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace Pupil {
@@ -26,10 +27,19 @@ inline constexpr const char *S_MAT_TYPE_NAME[] = { "diffuse", "dielectric", "rou
 
 namespace util {
 enum class ETextureType : int { RGB = 0, Bitmap = 1, Checkerboard = 2 };
+enum class ETextureAddressMode : int { Wrap = 0, Clamp = 1, Mirror = 2, Border = 3 }; // texture.h:10-15
+enum class ETextureFilterMode : int { Point = 0, Linear = 1 };                        // texture.h:17-20
+struct BitmapTexture { // texture.h:36-56: texels are owned by resource::TextureManager
+    size_t w = 0, h = 0;
+    const float *data = nullptr;
+    ETextureAddressMode address_mode = ETextureAddressMode::Wrap;
+    ETextureFilterMode filter_mode = ETextureFilterMode::Linear;
+};
 struct Texture {
     ETextureType type = ETextureType::RGB;
     Float3 rgb{ 0.f };              // RGB: color
     Float3 patch1{ 0.f }, patch2{ 0.f }; // checkerboard: xml color0 -> patch1, color1 -> patch2 (scene.cpp:170-172)
+    BitmapTexture bitmap;
     Transform transform;            // to_uv
 };
 }// namespace util
@@ -54,10 +64,25 @@ struct Material {
 };
 Material LoadMaterialFromXml(const xml::Object *obj, Scene *scene) noexcept;
 
+// resource/texture.{h,cpp}: images are loaded once per path and shared; "mem:KEY" names registered images
+class TextureManager : public util::Singleton<TextureManager> {
+public:
+    util::Texture GetTexture(std::string_view path) noexcept; // bitmap, or mid-grey RGB (with a warning) when the image cannot be read
+    bool RegisterImage(std::string_view key, const float *rgba, size_t w, size_t h) noexcept;
+    void Clear() noexcept;
+
+private:
+    struct ImageData {
+        size_t w = 0, h = 0;
+        std::vector<float> rgba;
+    };
+    std::unordered_map<std::string, std::unique_ptr<ImageData>> m_images;
+};
+
 enum class EEmitterType { Unknown, Area, Point, ConstEnv, EnvMap };
 struct Emitter {
     EEmitterType type = EEmitterType::Unknown;
-    util::Texture radiance;   // area
+    util::Texture radiance;   // area | env map (bitmap)
     util::Float3 color{ 0.f }; // const env radiance | point intensity
     util::Float3 position{ 0.f };
     float scale = 1.f;         // env map

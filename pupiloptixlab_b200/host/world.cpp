@@ -1,6 +1,9 @@
 #include "world.h"
 
+#include <cmath>
 #include <cstring>
+#include <map>
+#include <tuple>
 
 namespace Pupil {
 namespace {
@@ -12,12 +15,30 @@ float Max3(float r, float g, float b) { return r > g ? (r > b ? r : b) : (g > b 
 util::Float3 PixelAverage(const util::Texture &t) { // optix_material.cpp:9-36
     if (t.type == util::ETextureType::Checkerboard)
         return util::Float3{ (t.patch1.x + t.patch2.x) * 0.5f, (t.patch1.y + t.patch2.y) * 0.5f, (t.patch1.z + t.patch2.z) * 0.5f };
+    if (t.type == util::ETextureType::Bitmap) { // :19-30: running fp32 sums over all texels, then one division
+        float r = 0.f, g = 0.f, b = 0.f;
+        for (size_t i = 0, j = 0; i < t.bitmap.h; ++i)
+            for (size_t k = 0; k < t.bitmap.w; ++k, j += 4) r += t.bitmap.data[j], g += t.bitmap.data[j + 1], b += t.bitmap.data[j + 2];
+        const float inv = 1.0f / (1.f * t.bitmap.h * t.bitmap.w); // float3 / float multiplies by the reciprocal (cuda/vec_math.h:425-428)
+        return util::Float3{ r * inv, g * inv, b * inv };
+    }
     return t.rgb;
 }
 float SelectWeight(const util::Texture &t) { // world/emitter.cpp:77-101
     if (t.type == util::ETextureType::Checkerboard) return (Max3(t.patch1.x, t.patch1.y, t.patch1.z) + Max3(t.patch2.x, t.patch2.y, t.patch2.z)) * 0.5f;
+    if (t.type == util::ETextureType::Bitmap) { // :89-99 with the reference's own (i * w + j) indexing; indices past the image are skipped
+        float w = 0.f;
+        for (size_t i = 0; i < t.bitmap.w; i++)
+            for (size_t j = 0; j < t.bitmap.h; j++) {
+                const size_t px = i * t.bitmap.w + j;
+                if (px >= t.bitmap.w * t.bitmap.h) continue;
+                w += Max3(t.bitmap.data[px * 4 + 0], t.bitmap.data[px * 4 + 1], t.bitmap.data[px * 4 + 2]);
+            }
+        return w / (1.f * t.bitmap.w * t.bitmap.h);
+    }
     return Max3(t.rgb.x, t.rgb.y, t.rgb.z);
 }
+std::map<std::tuple<const float *, size_t, size_t, int, int>, uint64_t> g_device_bitmaps;
 }// namespace
 
 namespace optix::material {
@@ -26,9 +47,28 @@ float DiffuseFresnelReflectance(float eta) noexcept {
     const float i1 = 1.0f / eta, i2 = i1 * i1, i3 = i2 * i1, i4 = i3 * i1, i5 = i4 * i1;  // d'Eon & Irving 2011
     return 0.919317f - 3.4793f * i1 + 6.75335f * i2 - 7.80989f * i3 + 4.98554f * i4 - 1.36881f * i5;
 }
+uint64_t GetDeviceBitmap(const util::BitmapTexture &b) noexcept {
+    if (!b.data || !b.w || !b.h) return 0;
+    const auto key = std::make_tuple(b.data, b.w, b.h, static_cast<int>(b.address_mode), static_cast<int>(b.filter_mode));
+    auto it = g_device_bitmaps.find(key);
+    if (it != g_device_bitmaps.end()) return it->second;
+    uint64_t handle = 0;
+    if (pb2_device_count() > 0)
+        Pb2Check(pb2_bitmap_create(b.data, static_cast<uint32_t>(b.w), static_cast<uint32_t>(b.h), static_cast<int>(b.address_mode),
+                                   static_cast<int>(b.filter_mode), &handle),
+                 "pb2_bitmap_create");
+    g_device_bitmaps[key] = handle;
+    return handle;
+}
+void ClearDeviceBitmaps() noexcept {
+    for (auto &kv : g_device_bitmaps)
+        if (kv.second) pb2_bitmap_destroy(kv.second);
+    g_device_bitmaps.clear();
+}
 pb2_texture ToDeviceTexture(const util::Texture &tex) noexcept {
     pb2_texture t{};
     t.type = static_cast<int32_t>(tex.type);
+    if (tex.type == util::ETextureType::Bitmap) t.bitmap = GetDeviceBitmap(tex.bitmap);
     const util::Float3 a = tex.type == util::ETextureType::Checkerboard ? tex.patch1 : tex.rgb;
     for (int c = 0; c < 3; ++c) t.a[c] = a.e[c], t.b[c] = tex.patch2.e[c];
     for (int c = 0; c < 4; ++c) t.r0[c] = tex.transform.matrix.re[0][c], t.r1[c] = tex.transform.matrix.re[1][c];
@@ -112,7 +152,45 @@ void CameraHelper::Upload(pb2_scene *scene) noexcept {
 void EmitterHelper::Clear() noexcept {
     m_areas.clear();
     m_env = pb2_emitter{};
+    m_row_cdf.clear(), m_row_weight.clear(), m_col_cdf.clear();
+    FreeEnvTables();
     m_dirty = true;
+}
+void EmitterHelper::FreeEnvTables() noexcept {
+    if (m_env_tables_device) pb2_free(m_env_tables_device);
+    m_env_tables_device = nullptr;
+}
+// world/emitter.cpp:107-149, statement for statement (fp32 running sums in the same order)
+void EmitterHelper::BuildEnvMapCdfTable(const resource::Emitter &emitter) noexcept {
+    const size_t w = emitter.radiance.bitmap.w, h = emitter.radiance.bitmap.h;
+    const float *data = emitter.radiance.bitmap.data;
+    constexpr float kPi = 3.14159265358979323846f;
+    m_col_cdf.resize((w + 1) * h);
+    m_row_cdf.resize(h + 1);
+    m_row_weight.resize(h);
+    size_t col_index = 0, row_index = 0;
+    float row_sum = 0.f;
+    m_row_cdf[row_index++] = 0.f;
+    for (auto y = 0u; y < h; ++y) {
+        float col_sum = 0.f;
+        m_col_cdf[col_index++] = 0.f;
+        for (auto x = 0u; x < w; ++x) {
+            const auto pixel_index = y * w + x;
+            col_sum += Luminance(util::Float3{ data[pixel_index * 4 + 0], data[pixel_index * 4 + 1], data[pixel_index * 4 + 2] });
+            m_col_cdf[col_index++] = col_sum;
+        }
+        for (auto x = 1u; x < w; ++x) m_col_cdf[col_index - x - 1] /= col_sum;
+        m_col_cdf[col_index - 1] = 1.f;
+        const float weight = std::sin((y + 0.5f) * kPi / h);
+        m_row_weight[y] = weight;
+        row_sum += col_sum * weight;
+        m_row_cdf[row_index++] = row_sum;
+    }
+    for (auto y = 1u; y < h; ++y) m_row_cdf[row_index - y - 1] /= row_sum;
+    m_row_cdf[row_index - 1] = 1.f;
+    if (row_sum == 0) Log::Warn("The environment map is completely black.");
+    m_env.normalization = 1.f / (row_sum * (2.f * kPi / w) * (kPi / h));
+    m_env.map_w = static_cast<uint32_t>(w), m_env.map_h = static_cast<uint32_t>(h);
 }
 void EmitterHelper::SetMeshAreaEmitter(const resource::ShapeInstance &ins, size_t offset) noexcept {
     const util::Mat4 &xf = ins.transform.matrix;
@@ -183,9 +261,26 @@ void EmitterHelper::AddEmitter(const resource::Emitter &emitter) noexcept {
         m_env.radiance.type = PB2_TEX_RGB;
         for (int c = 0; c < 3; ++c) m_env.radiance.a[c] = emitter.color.e[c];
         m_env.weight = 1.f;
+        const util::AABB aabb = util::Singleton<World>::instance()->GetAABB();
+        for (int c = 0; c < 3; ++c) m_env.center[c] = (aabb.max.e[c] + aabb.min.e[c]) * 0.5f;
+        m_dirty = true;
+    } else if (emitter.type == resource::EEmitterType::EnvMap && emitter.radiance.type == util::ETextureType::Bitmap) { // :293-312
+        m_env = pb2_emitter{};
+        m_env.type = PB2_EMIT_ENV_MAP;
+        m_env.radiance = optix::material::ToDeviceTexture(emitter.radiance);
+        m_env.scale = emitter.scale;
+        const util::AABB aabb = util::Singleton<World>::instance()->GetAABB();
+        for (int c = 0; c < 3; ++c) m_env.center[c] = (aabb.max.e[c] + aabb.min.e[c]) * 0.5f;
+        m_env.weight = 1.f;
+        const util::Mat4 &m = emitter.transform.matrix;
+        const util::Mat4 to_local = m.GetInverse();
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) m_env.to_world[r * 3 + c] = m.re[r][c], m_env.to_local[r * 3 + c] = to_local.re[r][c];
+        BuildEnvMapCdfTable(emitter);
+        FreeEnvTables();
         m_dirty = true;
     }
-    // point emitters are parsed but never sampled by the reference; env maps need image IO (not built)
+    // point emitters are parsed but never sampled by the reference
 }
 void EmitterHelper::ComputeProbability() noexcept { // world/emitter.cpp:321-337
     float area_weight_sum = 0.f;
@@ -199,6 +294,17 @@ void EmitterHelper::ComputeProbability() noexcept { // world/emitter.cpp:321-337
 }
 void EmitterHelper::Upload(pb2_scene *scene) noexcept {
     if (!m_dirty || !scene) return;
+    if (m_env.type == PB2_EMIT_ENV_MAP && !m_env_tables_device) { // :362-376: one allocation, row_cdf | row_weight | col_cdf
+        const size_t n_row = m_row_cdf.size(), n_w = m_row_weight.size(), n_col = m_col_cdf.size();
+        Pb2Check(pb2_malloc(&m_env_tables_device, (n_row + n_w + n_col) * sizeof(float)), "pb2_malloc(env tables)");
+        if (m_env_tables_device) {
+            float *d = static_cast<float *>(m_env_tables_device);
+            pb2_upload(d, m_row_cdf.data(), n_row * sizeof(float));
+            pb2_upload(d + n_row, m_row_weight.data(), n_w * sizeof(float));
+            pb2_upload(d + n_row + n_w, m_col_cdf.data(), n_col * sizeof(float));
+        }
+        m_env.env_tables = static_cast<const float *>(m_env_tables_device);
+    }
     Pb2Check(pb2_scene_set_emitters(scene, m_areas.data(), (uint32_t)m_areas.size(), GetEnvEmitter()), "pb2_scene_set_emitters");
     m_dirty = false;
 }
@@ -267,6 +373,8 @@ void World::Destroy() noexcept {
     scene.reset(), camera.reset(), emitters.reset();
     if (m_pb2) pb2_scene_destroy(m_pb2), m_pb2 = nullptr;
     util::Singleton<resource::ShapeManager>::instance()->Clear();
+    optix::material::ClearDeviceBitmaps();
+    util::Singleton<resource::TextureManager>::instance()->Clear();
 }
 bool World::LoadScene(std::filesystem::path path) noexcept {
     if (!std::filesystem::exists(path)) {

@@ -22,6 +22,9 @@ namespace optix::material {
 // host precompute of one material: eta = int/ext, plastic sampling weight and internal diffuse reflectance
 pb2_material LoadMaterial(const resource::Material &mat) noexcept;
 pb2_texture ToDeviceTexture(const util::Texture &tex) noexcept; // CudaTextureManager::GetCudaTexture, cuda/texture.cpp:104-131
+// CudaTextureManager::GetCudaTextureObject / Clear (cuda/texture.cpp:60-102,133-143): one texture object per (image, modes)
+uint64_t GetDeviceBitmap(const util::BitmapTexture &bitmap) noexcept; // 0 when no device is present (host-only parse)
+void ClearDeviceBitmaps() noexcept;
 float DiffuseFresnelReflectance(float eta) noexcept;           // fresnel::DiffuseReflectance, fresnel.h:58-84
 }// namespace optix::material
 
@@ -54,6 +57,7 @@ private:
 
 class EmitterHelper {
 public:
+    ~EmitterHelper() { FreeEnvTables(); }
     void Clear() noexcept;
     size_t AddAreaEmitter(const resource::ShapeInstance &ins) noexcept; // returns the table size afterwards
     void ResetAreaEmitter(const resource::ShapeInstance &ins, size_t offset) noexcept;
@@ -61,14 +65,22 @@ public:
     void ComputeProbability() noexcept;
     const std::vector<pb2_emitter> &GetAreaEmitters() const noexcept { return m_areas; }
     const pb2_emitter *GetEnvEmitter() const noexcept { return m_env.type == PB2_EMIT_NONE ? nullptr : &m_env; }
+    // host copies of the env-map tables (BuildEnvMapCdfTable): row_cdf[h + 1], row_weight[h], col_cdf[(w + 1) * h]
+    const std::vector<float> &GetEnvRowCdf() const noexcept { return m_row_cdf; }
+    const std::vector<float> &GetEnvRowWeight() const noexcept { return m_row_weight; }
+    const std::vector<float> &GetEnvColCdf() const noexcept { return m_col_cdf; }
     // replaces GetEmitterGroup(): uploads the table when it changed
     void Upload(pb2_scene *scene) noexcept;
 
 private:
     void SetMeshAreaEmitter(const resource::ShapeInstance &ins, size_t offset) noexcept;
     void SetSphereAreaEmitter(const resource::ShapeInstance &ins, size_t offset) noexcept;
+    void BuildEnvMapCdfTable(const resource::Emitter &emitter) noexcept;
+    void FreeEnvTables() noexcept;
     std::vector<pb2_emitter> m_areas;
     pb2_emitter m_env{};
+    std::vector<float> m_row_cdf, m_row_weight, m_col_cdf;
+    void *m_env_tables_device = nullptr; // m_env_cdf_weight_cuda_memory of the reference (world/emitter.cpp:362-376)
     bool m_dirty = true;
 };
 

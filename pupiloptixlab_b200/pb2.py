@@ -29,7 +29,7 @@ class Pb2Error(RuntimeError):
 
 
 class Texture(C.Structure):
-    _fields_ = [("type", i32), ("a", f32 * 3), ("b", f32 * 3), ("r0", f32 * 4), ("r1", f32 * 4)]
+    _fields_ = [("type", i32), ("a", f32 * 3), ("b", f32 * 3), ("r0", f32 * 4), ("r1", f32 * 4), ("pad0", u32), ("bitmap", u64)]
 
 
 class Material(C.Structure):
@@ -39,7 +39,9 @@ class Material(C.Structure):
 
 class Emitter(C.Structure):
     _fields_ = [("type", i32), ("weight", f32), ("select_probability", f32), ("radiance", Texture), ("area", f32),
-                ("pos", (f32 * 3) * 3), ("nrm", (f32 * 3) * 3), ("uv", (f32 * 2) * 3), ("center", f32 * 3), ("radius", f32)]
+                ("pos", (f32 * 3) * 3), ("nrm", (f32 * 3) * 3), ("uv", (f32 * 2) * 3), ("center", f32 * 3), ("radius", f32),
+                ("scale", f32), ("normalization", f32), ("map_w", u32), ("map_h", u32), ("to_world", f32 * 9), ("to_local", f32 * 9),
+                ("env_tables", C.c_void_p)]
 
 
 class Hit(C.Structure):
@@ -85,7 +87,8 @@ def lib():
         P, vp = C.POINTER, C.c_void_p
         L.pb2_last_error.restype = C.c_char_p
         sigs = {
-            "pb2_init": [C.c_int], "pb2_device_count": [], "pb2_malloc": [P(vp), u64], "pb2_free": [vp], "pb2_trim": [], "pb2_upload": [vp, vp, u64],
+            "pb2_init": [C.c_int], "pb2_device_count": [], "pb2_malloc": [P(vp), u64], "pb2_free": [vp], "pb2_trim": [], "pb2_bitmap_create": [vp, u32, u32, C.c_int, C.c_int, P(u64)],
+            "pb2_bitmap_destroy": [u64], "pb2_upload": [vp, vp, u64],
             "pb2_download": [vp, vp, u64], "pb2_memset": [vp, C.c_int, u64], "pb2_scene_create": [P(vp)], "pb2_scene_destroy": [vp],
             "pb2_scene_clear": [vp], "pb2_scene_set_stream": [vp, vp],
             "pb2_scene_add_mesh": [vp, vp, vp, vp, vp, u32, u32, P(u32)],
@@ -146,6 +149,28 @@ class DeviceBuffer:
         if self.ptr:
             lib().pb2_free(self.ptr)
             self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Bitmap:
+    """pb2_bitmap_create: a float4 texture object (normalised coordinates); `handle` goes into Texture.bitmap"""
+
+    def __init__(self, rgba: np.ndarray, address_mode: int = 0, filter_mode: int = 1):
+        img = np.ascontiguousarray(rgba, np.float32)
+        assert img.ndim == 3 and img.shape[2] == 4
+        h = u64()
+        check(lib().pb2_bitmap_create(_ptr(img), img.shape[1], img.shape[0], address_mode, filter_mode, C.byref(h)))
+        self.handle = h.value
+
+    def free(self):
+        if self.handle:
+            lib().pb2_bitmap_destroy(self.handle)
+            self.handle = 0
 
     def __del__(self):
         try:

@@ -53,6 +53,9 @@ def lib():
             "pupil_get_emitters": [P(pb2.Emitter), P(pb2.Emitter), P(i32)], "pupil_scene_handle": [P(vp)], "pupil_set_bvh_builder": [C.c_int],
             "pupil_build_stats": [P(pb2.BuildStats)], "pupil_render_stats": [P(pb2.RenderStats)], "pupil_camera_move": [f32, f32, f32],
             "pupil_camera_rotate": [f32, f32], "pupil_camera_set_fov": [f32],
+            "pupil_register_image": [C.c_char_p, vp, u32, u32], "pupil_image_load": [C.c_char_p, P(u32), P(u32), vp, u64],
+            "pupil_image_save": [C.c_char_p, vp, u32, u32, C.c_int], "pupil_save_buffer": [C.c_char_p, C.c_char_p, C.c_int],
+            "pupil_get_env_tables": [P(u32), P(u32), vp, vp, vp],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -105,8 +108,45 @@ def load_scene(desc: SceneDesc, host_only: bool = False):
         T = None if m.get("texcoords") is None else np.ascontiguousarray(m["texcoords"], np.float32)
         check(lib().pupil_register_mesh(key.encode(), pb2._ptr(P), pb2._ptr(N), pb2._ptr(T), pb2._ptr(I), P.shape[0], I.shape[0]))
         names[i] = key
+    from . import scenes as _scenes
+    for t in _scenes.images_of(desc):  # bitmap textures / env maps that carry their texels in memory
+        img = np.ascontiguousarray(t.image, np.float32)
+        check(lib().pupil_register_image(_scenes.image_name(t).encode(), pb2._ptr(img), img.shape[1], img.shape[0]))
     fn = lib().pupil_parse_scene_xml_string if host_only else lib().pupil_load_scene_xml_string
     check(fn(to_xml_string(desc, names).encode(), None))
+
+
+IMAGE_FORMATS = dict(hdr=0, exr=1, pfm=2)
+
+
+def image_load(path) -> np.ndarray:
+    """util::BitmapTexture::Load: float32 (H, W, 4), row 0 = first row of the file; 8-bit sources linearised (gamma 2.2)"""
+    w, h = u32(), u32()
+    check(lib().pupil_image_load(str(path).encode(), C.byref(w), C.byref(h), None, 0))
+    out = np.zeros((h.value, w.value, 4), np.float32)
+    check(lib().pupil_image_load(str(path).encode(), C.byref(w), C.byref(h), pb2._ptr(out), out.size))
+    return out
+
+
+def image_save(path, rgba: np.ndarray, fmt: str | None = None):
+    """util::BitmapTexture::Save: rgba (H, W, 4) with row 0 = BOTTOM of the picture (frame-buffer order)"""
+    img = np.ascontiguousarray(rgba, np.float32)
+    fmt = fmt or str(path).rsplit(".", 1)[-1].lower()
+    check(lib().pupil_image_save(str(path).encode(), pb2._ptr(img), img.shape[1], img.shape[0], IMAGE_FORMATS[fmt]))
+
+
+def save_buffer(name: str, path, fmt: str | None = None):
+    fmt = fmt or str(path).rsplit(".", 1)[-1].lower()
+    check(lib().pupil_save_buffer(name.encode(), str(path).encode(), IMAGE_FORMATS[fmt]))
+
+
+def env_tables():
+    """(row_cdf[h+1], row_weight[h], col_cdf[h, w+1]) of the scene's env-map emitter"""
+    w, h = u32(), u32()
+    check(lib().pupil_get_env_tables(C.byref(w), C.byref(h), None, None, None))
+    rc, rw, cc = np.zeros(h.value + 1, np.float32), np.zeros(h.value, np.float32), np.zeros((h.value, w.value + 1), np.float32)
+    check(lib().pupil_get_env_tables(C.byref(w), C.byref(h), pb2._ptr(rc), pb2._ptr(rw), pb2._ptr(cc)))
+    return rc, rw, cc
 
 
 def pass_config(max_depth: int = 0, accumulate: bool = True, frames_per_run: int = 1, first_seed: int = 0, seed_stride: int = 1,

@@ -27,11 +27,25 @@ MAT_NAMES = ("diffuse", "dielectric", "roughdielectric", "conductor", "roughcond
 
 @dataclass
 class Tex:
-    """<rgb> (kind='rgb', color0) or <texture type="checkerboard"> (color0/color1 + to_uv scale)."""
+    """<rgb> (kind='rgb', color0), <texture type="checkerboard"> (color0/color1 + to_uv scale) or
+    <texture type="bitmap"> (image: float32 (H, W, 4) linear texels, row 0 = first row of the file; or filename)."""
     kind: str = "rgb"
     color0: Sequence[float] = (0.5, 0.5, 0.5)
     color1: Sequence[float] = (0.2, 0.2, 0.2)
     uv_scale: Optional[Sequence[float]] = None
+    image: Optional[np.ndarray] = None
+    filename: Optional[str] = None      # written to the XML when set; otherwise the image is registered in memory
+    filter_type: str = "bilinear"       # bilinear | nearest   (resource/scene.cpp:151-155)
+    wrap_mode: str = "repeat"           # repeat | mirror | clamp (scene.cpp:157-165)
+
+
+@dataclass
+class EnvMap:
+    """<emitter type="envmap">: lat-long radiance image + scale + to_world (resource/scene.cpp:207-219)."""
+    image: Optional[np.ndarray] = None  # float32 (H, W, 4)
+    filename: Optional[str] = None
+    scale: float = 1.0
+    to_world: Optional["Xf"] = None
 
 
 @dataclass
@@ -86,6 +100,7 @@ class SceneDesc:
     sensor: Sensor = field(default_factory=Sensor)
     shapes: list = field(default_factory=list)
     env_radiance: Optional[Sequence[float]] = None
+    env_map: Optional[EnvMap] = None
     name: str = "scene"
 
     def num_triangles(self) -> int:
@@ -174,6 +189,40 @@ def material_grid(width: int = 1920, height: int = 1080, max_depth: int = 8, nx:
     return SceneDesc(max_depth=max_depth, sensor=sensor, shapes=shapes, env_radiance=env, name="material_grid")
 
 
+def procedural_image(w: int, h: int, seed: int, hdr: bool = False) -> np.ndarray:
+    """deterministic float32 (h, w, 4) texels: gradients + noise, plus a bright sun lobe when hdr (env maps)"""
+    rng = np.random.default_rng(seed)
+    y, x = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
+    img = np.zeros((h, w, 4), np.float32)
+    img[..., 0] = 0.25 + 0.5 * x / max(w - 1, 1)
+    img[..., 1] = 0.2 + 0.6 * y / max(h - 1, 1)
+    img[..., 2] = 0.5 + 0.35 * np.sin(x * 0.5) * np.cos(y * 0.8)
+    img[..., :3] += rng.random((h, w, 3), dtype=np.float32) * np.float32(0.1)
+    if hdr:
+        img[..., :3] += (30.0 * np.exp(-((x - 0.7 * w) ** 2 + (y - 0.3 * h) ** 2) / (0.01 * w * w)))[..., None].astype(np.float32)
+    img[..., 3] = 1.0
+    return np.ascontiguousarray(img.astype(np.float32))
+
+
+def envmap_scene(width: int = 1920, height: int = 1080, max_depth: int = 8, env_w: int = 64, env_h: int = 32) -> SceneDesc:
+    """Bitmap-textured floor and spheres under a lat-long environment map (rows a18 / a19 of SURVEY.md 8: bitmap
+    texture sampling and the EnvMapEmitter), with one small area light so both emitter kinds are selected."""
+    floor_tex = Tex("bitmap", image=procedural_image(32, 32, 5), filter_type="bilinear", wrap_mode="repeat", uv_scale=(4.0, 4.0, 1.0))
+    ball_tex = Tex("bitmap", image=procedural_image(16, 8, 6), filter_type="nearest", wrap_mode="mirror")
+    shapes = [
+        Shape("rectangle", Xf("srt", scale=(6.0, 6.0, 1.0), rotate_axis=(1, 0, 0), rotate_angle=-90.0), Bsdf("diffuse", True, dict(reflectance=floor_tex)), name="floor"),
+        Shape("sphere", None, Bsdf("plastic", False, dict(diffuse_reflectance=ball_tex, int_ior=1.5, ext_ior=1.0)), center=(-1.6, 0.8, 0.0), radius=0.8, name="ball_tex"),
+        Shape("sphere", None, Bsdf("roughconductor", False, dict(alpha=0.2, eta=(0.200438, 0.924033, 1.10221), k=(3.91295, 2.45285, 2.14219))),
+              center=(0.2, 0.8, 0.3), radius=0.8, name="ball_metal"),
+        Shape("sphere", None, Bsdf("dielectric", False, dict(int_ior=1.5, ext_ior=1.0)), center=(2.0, 0.8, -0.2), radius=0.8, name="ball_glass"),
+        Shape("rectangle", Xf("srt", scale=(0.4, 0.4, 1.0), rotate_axis=(1, 0, 0), rotate_angle=90.0, translate=(0.0, 3.5, 0.0)),
+              Bsdf("diffuse", True, dict(reflectance=(0.0, 0.0, 0.0))), emitter=(6.0, 5.0, 4.0), name="lamp"),
+    ]
+    sensor = Sensor(fov=45.0, fov_axis="x", to_world=Xf("lookat", origin=(0.0, 2.2, 6.5), target=(0.0, 0.7, 0.0), up=(0, 1, 0)), width=width, height=height)
+    env = EnvMap(image=procedural_image(env_w, env_h, 7, hdr=True), scale=1.25, to_world=Xf("srt", rotate_axis=(0, 1, 0), rotate_angle=40.0))
+    return SceneDesc(max_depth=max_depth, sensor=sensor, shapes=shapes, env_map=env, name="envmap_scene")
+
+
 def heightfield_mesh(n: int, seed: int = 42, size: float = 20.0, amplitude: float = 1.2) -> dict:
     """(n+1)^2 vertices, 2*n*n triangles: a sum of seeded sinusoids (deterministic, no file IO)."""
     rng = np.random.default_rng(seed)
@@ -238,11 +287,31 @@ def _tex_xml(name: str, t, ind: str) -> str:
         return f'{ind}<rgb name="{name}" value="{_csv(t)}" />\n'
     if t.kind == "rgb":
         return f'{ind}<rgb name="{name}" value="{_csv(t.color0)}" />\n'
-    s = f'{ind}<texture name="{name}" type="checkerboard">\n'
-    s += f'{ind}\t<rgb name="color0" value="{_csv(t.color0)}" />\n{ind}\t<rgb name="color1" value="{_csv(t.color1)}" />\n'
+    if t.kind == "bitmap":
+        s = f'{ind}<texture name="{name}" type="bitmap">\n{ind}\t<string name="filename" value="{image_name(t)}" />\n'
+        s += f'{ind}\t<string name="filter_type" value="{t.filter_type}" />\n{ind}\t<string name="wrap_mode" value="{t.wrap_mode}" />\n'
+    else:
+        s = f'{ind}<texture name="{name}" type="checkerboard">\n'
+        s += f'{ind}\t<rgb name="color0" value="{_csv(t.color0)}" />\n{ind}\t<rgb name="color1" value="{_csv(t.color1)}" />\n'
     if t.uv_scale is not None:
         s += f'{ind}\t<transform name="to_uv">\n{ind}\t\t<scale x="{_f(t.uv_scale[0])}" y="{_f(t.uv_scale[1])}" z="{_f(t.uv_scale[2])}" />\n{ind}\t</transform>\n'
     return s + f"{ind}</texture>\n"
+
+
+def image_name(t) -> str:
+    """file name of a bitmap texture / env map: its own, or the key the in-memory image is registered under"""
+    return t.filename if t.filename else f"mem:image_{id(t.image):x}"
+
+
+def images_of(scene: "SceneDesc") -> list:
+    """every Tex(kind='bitmap') / EnvMap of the scene that carries its texels in memory"""
+    out = []
+    for sh in scene.shapes:
+        cands = [sh.emitter] + (list(sh.bsdf.params.values()) if sh.bsdf is not None else [])
+        out += [c for c in cands if isinstance(c, Tex) and c.kind == "bitmap" and c.filename is None]
+    if scene.env_map is not None and scene.env_map.filename is None:
+        out.append(scene.env_map)
+    return out
 
 
 def _xf_xml(x: Optional[Xf], ind: str) -> str:
@@ -330,6 +399,10 @@ def to_xml_string(scene: SceneDesc, obj_names: dict) -> str:
         s += "\t</shape>\n"
     if scene.env_radiance is not None:
         s += f'\t<emitter type="constant">\n\t\t<rgb name="radiance" value="{_csv(scene.env_radiance)}" />\n\t</emitter>\n'
+    if scene.env_map is not None:
+        em = scene.env_map
+        s += f'\t<emitter type="envmap">\n\t\t<string name="filename" value="{image_name(em)}" />\n\t\t<float name="scale" value="{_f(em.scale)}" />\n'
+        s += _xf_xml(em.to_world, "\t\t") + "\t</emitter>\n"
     s += "</scene>\n"
     return s
 

@@ -95,6 +95,44 @@ def emitters():
     return out
 
 
+def test_image(w, h, seed, hdr=False):
+    """deterministic float32 (h, w, 4) texels: smooth gradients + noise (+ a bright lobe when hdr)"""
+    rng = np.random.default_rng(seed)
+    y, x = np.meshgrid(np.arange(h, dtype=F), np.arange(w, dtype=F), indexing="ij")
+    img = np.zeros((h, w, 4), F)
+    img[..., 0] = 0.2 + 0.6 * x / max(w - 1, 1)
+    img[..., 1] = 0.1 + 0.8 * y / max(h - 1, 1)
+    img[..., 2] = 0.5 + 0.4 * np.sin(x * 0.7) * np.cos(y * 0.9)
+    img[..., :3] += rng.random((h, w, 3), dtype=F) * F(0.15)
+    if hdr:
+        img[..., :3] += (40.0 * np.exp(-((x - 0.7 * w) ** 2 + (y - 0.3 * h) ** 2) / (0.02 * w * w)))[..., None].astype(F)
+    img[..., 3] = 1.0
+    return np.ascontiguousarray(img.astype(F))
+
+
+_ENV_KEEP = []
+
+
+def env_map_emitter(lib, img, scale=1.5, rotate_deg=30.0):
+    """orc.Emitter of type env map over `img`, tables built by the library itself (padded like orc scenes pad them)"""
+    h, w = img.shape[:2]
+    rc, rw, cc = np.zeros(h + 2, F), np.zeros(h + 1, F), np.zeros((h + 1) * (w + 1), F)
+    norm = lib.orc_build_env_tables(orc.fp(img), w, h, orc.fp(rc), orc.fp(rw), orc.fp(cc))
+    rc[h + 1], rw[h], cc[h * (w + 1):] = 1.0, rw[h - 1], cc[(h - 1) * (w + 1):h * (w + 1)]
+    _ENV_KEEP.append((img, rc, rw, cc))
+    e = orc.Emitter()
+    e.type, e.weight, e.select_probability = orc.EMIT_ENV_MAP, 1.0, 0.25
+    from pupiloptixlab_b200.scenes import Tex
+    e.radiance = orc.make_texture(Tex("bitmap", image=img, filter_type="bilinear", wrap_mode="repeat"))
+    e.scale, e.normalization, e.map_w, e.map_h = scale, norm, w, h
+    a = np.deg2rad(rotate_deg)
+    m = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]], F)
+    e.to_world[:] = [float(v) for v in m.reshape(-1)]
+    e.to_local[:] = [float(v) for v in m.T.reshape(-1)]
+    e.row_cdf, e.row_weight, e.col_cdf = orc.fp(rc), orc.fp(rw), orc.fp(cc)
+    return e
+
+
 def run(lib) -> dict[str, np.ndarray]:
     P = C.POINTER
     R: dict[str, np.ndarray] = {}
@@ -161,6 +199,19 @@ def run(lib) -> dict[str, np.ndarray]:
     for i, (a, b) in enumerate(UV):
         lib.orc_tex_sample(C.byref(tex), float(a), float(b), orc.fp(to[i]))
     R["tex_uv"], R["tex_checker"] = UV, to
+    # bitmap: every address / filter mode over the same uv set (tex2D rules of orc_tex2d.h), with a to_uv scale
+    img = test_image(13, 7, 21)
+    UVB = np.concatenate([UV, np.random.default_rng(22).uniform(-2.5, 3.5, (200, 2)).astype(F)]).astype(F)
+    R["texbmp_uv"] = UVB
+    for wrap in ("repeat", "clamp", "mirror"):
+        for filt in ("nearest", "bilinear"):
+            tb = orc.make_texture(Tex("bitmap", image=img, filter_type=filt, wrap_mode=wrap, uv_scale=(1.5, 0.75, 1.0)))
+            tb.to_uv[0], tb.to_uv[5] = 1.5, 0.75
+            o = np.zeros((len(UVB), 3), F)
+            for i, (a, b) in enumerate(UVB):
+                lib.orc_tex_sample(C.byref(tb), float(a), float(b), orc.fp(o[i]))
+            R[f"texbmp_{wrap}_{filt}"] = o
+    R["texbmp_weight"] = np.array([lib.orc_texture_weight(C.byref(orc.make_texture(Tex("bitmap", image=im)))) for im in (img, test_image(5, 9, 3), test_image(8, 8, 4))], F)
     # ---- BSDFs: Sample over (material, wo, rng state) and Eval over (material, wi, wo) ----
     mats = local_bsdfs()
     WO2 = unit_vectors(40, 6)      # both hemispheres: back-facing wo must be handled like the reference
@@ -199,6 +250,26 @@ def run(lib) -> dict[str, np.ndarray]:
             lib.orc_emitter_eval(C.byref(e), orc.fp(pos), orc.fp(nrm), orc.fp(uv), orc.fp(HP[i]), orc.fp(rad), C.byref(pdf))
             EV[k, i, :3], EV[k, i, 3] = rad, pdf.value
     R["emit_hit_pos"], R["emit_hit_n"], R["emit_xi"], R["emit_sample"], R["emit_eval"] = HP, HN, XI, SD, EV
+    # ---- environment map: tables (BuildEnvMapCdfTable), SampleDirect, Eval ----
+    env_img = test_image(16, 8, 31, hdr=True)
+    eh, ew = env_img.shape[:2]
+    rc, rw, cc = np.zeros(eh + 1, F), np.zeros(eh, F), np.zeros(eh * (ew + 1), F)
+    R["env_normalization"] = np.array([lib.orc_build_env_tables(orc.fp(env_img), ew, eh, orc.fp(rc), orc.fp(rw), orc.fp(cc))], F)
+    R["env_row_cdf"], R["env_row_weight"], R["env_col_cdf"] = rc, rw, cc
+    env = env_map_emitter(lib, env_img)
+    XE = np.concatenate([np.random.default_rng(12).random((96, 2)), [[0.0, 0.0], [0.999999, 0.999999], [1e-6, 0.5], [0.5, 1e-6]]]).astype(F)
+    DIRS = unit_vectors(len(XE), 13)
+    ES, EE = np.zeros((len(XE), 8), F), np.zeros((len(XE), 4), F)
+    zero3 = np.zeros(3, F)
+    for i in range(len(XE)):
+        es = orc.EmitSample()
+        lib.orc_emitter_sample_direct(C.byref(env), orc.fp(HP[i % 32]), orc.fp(HN[i % 32]), float(XE[i, 0]), float(XE[i, 1]), C.byref(es))
+        ES[i] = list(es.radiance) + list(es.wi) + [es.distance, es.pdf]
+        rad, pdf = np.zeros(3, F), C.c_float()
+        pos = (HP[i % 32] + DIRS[i]).astype(F)
+        lib.orc_emitter_eval(C.byref(env), orc.fp(pos), orc.fp(zero3), orc.fp(np.zeros(2, F)), orc.fp(HP[i % 32]), orc.fp(rad), C.byref(pdf))
+        EE[i, :3], EE[i, 3] = rad, pdf.value
+    R["env_xi"], R["env_dirs"], R["env_sample"], R["env_eval"] = XE, DIRS, ES, EE
     arr = (orc.Emitter * 3)(*ems[:3])
     ps = np.concatenate([np.linspace(0, 1, 33), [0.3, 0.5, 0.9, 0.90000004]]).astype(F)
     R["select_p"] = ps
@@ -216,6 +287,7 @@ def render_cases():
         ("cornell48x32_d4", scenes.cornell_box(48, 32, 4), 2),
         ("grid96x54_d8", scenes.material_grid(96, 54, 8), 2),
         ("grid64x36_noarea_d6", scenes.material_grid(64, 36, 6, nx=4, nz=2, with_area_light=False), 2),
+        ("envmap64x36_d6", scenes.envmap_scene(64, 36, 6), 2),
     ]
 
 

@@ -19,7 +19,9 @@ ORACLE = ROOT / "oracle"
 
 MAT = dict(unknown=0, diffuse=1, dielectric=2, roughdielectric=3, conductor=4, roughconductor=5, plastic=6, roughplastic=7)
 TEX_RGB, TEX_BITMAP, TEX_CHECKER = 0, 1, 2
-EMIT_TRI, EMIT_SPHERE, EMIT_CONST_ENV = 1, 2, 3
+EMIT_TRI, EMIT_SPHERE, EMIT_CONST_ENV, EMIT_ENV_MAP = 1, 2, 3, 4
+ADDR = dict(repeat=0, clamp=1, mirror=2)
+FILTER = dict(nearest=0, bilinear=1)
 SHAPE = dict(obj=1, sphere=2, cube=3, rectangle=4)
 XF_IDENTITY, XF_MATRIX16, XF_MATRIX9, XF_LOOKAT, XF_SRT = range(5)
 
@@ -27,7 +29,8 @@ f32, i32, u32 = C.c_float, C.c_int32, C.c_uint32
 
 
 class Texture(C.Structure):
-    _fields_ = [("type", i32), ("a", f32 * 3), ("b", f32 * 3), ("to_uv", f32 * 16)]
+    _fields_ = [("type", i32), ("a", f32 * 3), ("b", f32 * 3), ("to_uv", f32 * 16),
+                ("bitmap_w", i32), ("bitmap_h", i32), ("address_mode", i32), ("filter_mode", i32), ("bitmap", C.POINTER(f32))]
 
 
 class Material(C.Structure):
@@ -54,7 +57,9 @@ class BsdfResult(C.Structure):
 
 class Emitter(C.Structure):
     _fields_ = [("type", i32), ("weight", f32), ("select_probability", f32), ("radiance", Texture), ("area", f32),
-                ("pos", (f32 * 3) * 3), ("nrm", (f32 * 3) * 3), ("uv", (f32 * 2) * 3), ("center", f32 * 3), ("radius", f32)]
+                ("pos", (f32 * 3) * 3), ("nrm", (f32 * 3) * 3), ("uv", (f32 * 2) * 3), ("center", f32 * 3), ("radius", f32),
+                ("scale", f32), ("normalization", f32), ("map_w", u32), ("map_h", u32), ("to_world", f32 * 9), ("to_local", f32 * 9),
+                ("row_cdf", C.POINTER(f32)), ("row_weight", C.POINTER(f32)), ("col_cdf", C.POINTER(f32))]
 
 
 class EmitSample(C.Structure):
@@ -110,6 +115,11 @@ def _declare(lib):
                                   C.c_int, u32, u32, P(f32), P(f32), P(f32), P(u32)]
     lib.orc_add_shape.restype = C.c_int
     lib.orc_set_env_const.argtypes = [C.c_void_p, f32, f32, f32]
+    lib.orc_set_env_map.argtypes = [C.c_void_p, P(f32), u32, u32, f32, P(Transform)]
+    lib.orc_build_env_tables.argtypes = [P(f32), u32, u32, P(f32), P(f32), P(f32)]
+    lib.orc_build_env_tables.restype = f32
+    lib.orc_texture_weight.argtypes = [P(Texture)]
+    lib.orc_texture_weight.restype = f32
     lib.orc_finalize.argtypes = [C.c_void_p]
     lib.orc_get_camera.argtypes = [C.c_void_p, P(f32), P(f32), P(f32)]
     lib.orc_num_area_emitters.argtypes = [C.c_void_p]
@@ -173,6 +183,12 @@ def make_texture(t) -> Texture:
     if t.kind == "rgb":
         out.type = TEX_RGB
         out.a[:] = [float(x) for x in t.color0]
+    elif t.kind == "bitmap":  # texels are borrowed: t.image must outlive the oracle scene (it lives in the SceneDesc)
+        img = t.image
+        assert img.dtype == np.float32 and img.flags["C_CONTIGUOUS"] and img.ndim == 3 and img.shape[2] == 4
+        out.type = TEX_BITMAP
+        out.bitmap, out.bitmap_w, out.bitmap_h = fp(img), img.shape[1], img.shape[0]
+        out.address_mode, out.filter_mode = ADDR[t.wrap_mode], FILTER[t.filter_type]
     else:
         out.type = TEX_CHECKER
         out.a[:] = [float(x) for x in t.color0]
@@ -275,6 +291,10 @@ class OracleScene:
                               int(sh.flip_tex_coords), nv, nf, pos, nrm, uv, idx)
         if desc.env_radiance is not None:
             lib.orc_set_env_const(self.h, *[float(x) for x in desc.env_radiance])
+        if getattr(desc, "env_map", None) is not None:
+            em = desc.env_map
+            xf = make_transform(em.to_world)
+            lib.orc_set_env_map(self.h, fp(em.image), em.image.shape[1], em.image.shape[0], float(em.scale), C.byref(xf))
         lib.orc_finalize(self.h)
         self.w, self.h_px = int(s.width), int(s.height)
 
@@ -301,6 +321,10 @@ class OracleScene:
         if n:
             self.lib.orc_get_area_emitters(self.h, arr)
         return list(arr)[:n]
+
+    def env_emitter(self):
+        e = Emitter()
+        return e if self.lib.orc_get_env_emitter(self.h, C.byref(e)) else None
 
     def camera_rays(self, seed=0):
         rays = np.zeros((self.w * self.h_px, 8), np.float32)

@@ -105,6 +105,82 @@ def test_textures(ref):
     assert np.array_equal(out[~edge, :3], ref["tex_checker"][~edge])
 
 
+def _pb2_bitmap_texture(bitmap: pb2.Bitmap, r0=(1, 0, 0, 0), r1=(0, 1, 0, 0)) -> pb2.Texture:
+    t = pb2.Texture()
+    t.type, t.bitmap = pb2.TEX_BITMAP, bitmap.handle
+    t.r0[:], t.r1[:] = r0, r1
+    return t
+
+
+@pytest.mark.parametrize("wrap", ["repeat", "clamp", "mirror"])
+@pytest.mark.parametrize("filt", ["nearest", "bilinear"])
+def test_bitmap_textures_match_the_tex2d_rules(ref, wrap, filt):
+    """cuda::Texture::Sample's bitmap branch (tex2D<float4>, framework/cuda/texture.h:52-54) on the texture unit against
+    the oracle's restatement of the published fetch rules.  Stated tolerance: nearest = exact except for coordinates
+    within 1e-4 texel of a texel edge; bilinear = 1/256 of the local texel range (1.8 fixed-point weights) + 1e-6."""
+    img = kat.test_image(13, 7, 21)
+    bm = pb2.Bitmap(img, orc.ADDR[wrap], orc.FILTER[filt])
+    UV = ref["texbmp_uv"]
+    t = _pb2_bitmap_texture(bm, (1.5, 0, 0, 0), (0, 0.75, 0, 0))
+    arr = (pb2.Texture * len(UV))(*[t] * len(UV))
+    out = np.zeros((len(UV), 4), F)
+    pb2.kat("texture", arr, UV, None, len(UV), out)
+    want = ref[f"texbmp_{wrap}_{filt}"]
+    x, y = UV[:, 0].astype(np.float64) * 1.5 * 13, UV[:, 1].astype(np.float64) * 0.75 * 7
+    if filt == "nearest":
+        edge = (np.abs(x - np.round(x)) < 1e-3) | (np.abs(y - np.round(y)) < 1e-3)
+        assert edge.mean() < 0.2
+        assert np.array_equal(out[~edge, :3], want[~edge])
+    else:
+        spread = float(img[..., :3].max() - img[..., :3].min())
+        edge = (np.abs(x - 0.5 - np.round(x - 0.5)) < 1e-3) | (np.abs(y - 0.5 - np.round(y - 0.5)) < 1e-3)
+        err = np.abs(out[:, :3].astype(np.float64) - want)
+        assert err[~edge].max() <= spread / 256 + 1e-6, err[~edge].max()
+        assert np.median(err) < 1e-3
+    bm.free()
+
+
+def test_env_map_emitter(ref, port_lib):
+    """EnvMapEmitter::SampleDirect / Eval (framework/render/emitter/env.h:24-64): the sampled cell (direction) must be the
+    reference's exactly; radiance goes through the texture unit (bilinear: 1/256 of the texel range), pdf follows it."""
+    img = kat.test_image(16, 8, 31, hdr=True)
+    env = kat.env_map_emitter(port_lib, img)
+    h, w = img.shape[:2]
+    bm = pb2.Bitmap(img, 0, 1)
+    tables = np.concatenate([ref["env_row_cdf"], ref["env_row_weight"], ref["env_col_cdf"]]).astype(F)
+    dev = pb2.DeviceBuffer(tables.nbytes)
+    dev.upload(tables)
+    p = pb2.Emitter()
+    p.type, p.weight, p.select_probability = pb2.EMIT_ENV_MAP, 1.0, 0.25
+    p.radiance = _pb2_bitmap_texture(bm)
+    p.scale, p.normalization, p.map_w, p.map_h = env.scale, float(ref["env_normalization"][0]), w, h
+    p.to_world[:], p.to_local[:] = list(env.to_world), list(env.to_local)
+    p.env_tables = dev.ptr.value
+    XE, DIRS, HP, HN = ref["env_xi"], ref["env_dirs"], ref["emit_hit_pos"], ref["emit_hit_n"]
+    n = len(XE)
+    idx = np.arange(n) % 32
+    in1 = np.concatenate([HP[idx], HN[idx], XE], 1).astype(F)
+    in2 = np.zeros((n, 12), F)
+    in2[:, 0:3], in2[:, 8:11] = (HP[idx] + DIRS).astype(F), HP[idx]
+    arr = (pb2.Emitter * n)(*[p] * n)
+    out = np.zeros((n, 16), F)
+    pb2.kat("emitter", arr, in1, in2, n, out)
+    es, ee = ref["env_sample"], ref["env_eval"]
+    # xi exactly on a cdf entry may pick the neighbouring cell on the other side: none of the test points is
+    close(out[:, 3:6], es[:, 3:6], atol=5e-6)       # direction = cell choice: exact up to fp32 sin/cos
+    assert np.all(out[:, 6] == es[:, 6])            # MAX_DISTANCE
+    spread = float(img[..., :3].max() - img[..., :3].min()) * env.scale
+    assert np.abs(out[:, 0:3] - es[:, 0:3]).max() <= spread / 256 + 1e-5
+    lum = lambda c: 0.2126 * c[:, 0] + 0.7152 * c[:, 1] + 0.0722 * c[:, 2]
+    # pdf = lum(radiance) * weights: compare after dividing out the radiance each side saw
+    ok = lum(es[:, 0:3]) > 1e-3
+    close((out[:, 7] / lum(out[:, 0:3]))[ok], (es[:, 7] / lum(es[:, 0:3]))[ok], rtol=2e-4)
+    assert np.abs(out[:, 8:11] - ee[:, 0:3]).max() <= spread / 256 + 1e-5
+    ok = lum(ee[:, 0:3]) > 1e-3
+    close((out[:, 11] / lum(out[:, 8:11]))[ok], (ee[:, 3] / lum(ee[:, 0:3]))[ok], rtol=5e-4)
+    dev.free(), bm.free()
+
+
 def _kat_bsdf(b: orc.LocalBsdf) -> pb2.KatBsdf:
     k = pb2.KatBsdf()
     k.type, k.alpha, k.eta, k.int_fdr, k.specular_sampling_weight, k.nonlinear = b.type, b.alpha, b.eta, b.int_fdr, b.specular_sampling_weight, b.nonlinear

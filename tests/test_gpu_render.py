@@ -57,6 +57,31 @@ def test_one_frame_same_seed_parity(port_lib, name, maker, min_match):
     assert rs.shadow_rays <= ref["shadow_rays"] * 1.002
 
 
+def test_env_map_and_bitmap_scene_parity(port_lib):
+    """rows a18 / a19: bitmap textures (texture unit) + EnvMapEmitter through the whole path.  Bilinear lookups differ from
+    the oracle's fixed-point emulation by up to 1/256 of the local texel range, so the per-pixel bar is 2 % here."""
+    desc = scenes.envmap_scene(160, 90, 6)
+    pupil.load_scene(desc)
+    pupil.pass_config()
+    pupil.run(1)
+    ref = orc.OracleScene(port_lib, desc).render(1)
+    assert np.array_equal(pupil.buffer("test").reshape(-1), ref["test"])
+    assert np.abs(pupil.buffer("albedo").reshape(-1, 3) - ref["albedo"]).max() < 0.02
+    frame = pupil.buffer("final result")
+    assert np.isfinite(frame).all()
+    ok = _match(frame, ref["frame"], rel=2e-2)
+    assert ok.mean() >= 0.95, f"{ok.mean() * 100:.3f}% of pixels within tolerance"
+    gm, rm = frame[..., :3].mean(), ref["frame"][:, :3].mean()
+    assert abs(gm - rm) <= 0.01 * rm
+    # converged: 256 spp each side
+    pupil.pass_config(frames_per_run=256)
+    pupil.run(1)
+    g = pupil.buffer("pt accum buffer")[..., :3].reshape(-1, 3).astype(np.float64)
+    r = orc.OracleScene(port_lib, desc).render(256, threads=0)["accum"][:, :3].astype(np.float64)
+    relmse = float(np.mean((g - r) ** 2 / (r ** 2 + 1e-2)))
+    assert relmse < 1e-3, relmse
+
+
 def test_progressive_running_mean_and_batching(port_lib):
     """8 x OnRun(1 frame) == 1 x OnRun(8 frames) bit for bit (main.cu:190-196 running mean in frame order), and both
     follow the oracle's 8-frame accumulation"""

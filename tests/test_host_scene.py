@@ -61,6 +61,15 @@ def _check_against_oracle(desc, port_lib):
     assert (env is not None) == bool(has)
     if env is not None:
         assert env.type == oenv.type and list(env.radiance.a) == list(oenv.radiance.a) and env.select_probability == oenv.select_probability
+    if env is not None and env.type == pb2.EMIT_ENV_MAP:  # EmitterHelper::AddEmitter + BuildEnvMapCdfTable, world/emitter.cpp:107-149,293-312
+        assert env.radiance.type == pb2.TEX_BITMAP and oenv.radiance.type == orc.TEX_BITMAP
+        assert (env.map_w, env.map_h) == (oenv.map_w, oenv.map_h) and env.scale == oenv.scale and env.normalization == oenv.normalization
+        assert list(env.to_world) == list(oenv.to_world) and list(env.to_local) == list(oenv.to_local)
+        rc, rw, cc = pupil.env_tables()
+        h, w = env.map_h, env.map_w
+        assert np.array_equal(rc, np.ctypeslib.as_array(oenv.row_cdf, (h + 1,)))
+        assert np.array_equal(rw, np.ctypeslib.as_array(oenv.row_weight, (h,)))
+        assert np.array_equal(cc.reshape(-1), np.ctypeslib.as_array(oenv.col_cdf, (h * (w + 1),)))
     # emitter offsets: running sum over emitting instances (pt_pass.cpp:178-193)
     off = 0
     for inst, sh in zip(ins, desc.shapes):
@@ -73,7 +82,8 @@ def _check_against_oracle(desc, port_lib):
 
 
 @pytest.mark.parametrize("maker", [lambda: scenes.cornell_box(64, 48, 8), lambda: scenes.material_grid(96, 54, 6),
-                                   lambda: scenes.terrain(24, 80, 45, 5)], ids=["cornell", "material_grid", "terrain"])
+                                   lambda: scenes.terrain(24, 80, 45, 5), lambda: scenes.envmap_scene(64, 36, 6)],
+                         ids=["cornell", "material_grid", "terrain", "envmap"])
 def test_world_precompute_matches_oracle(port_lib, maker):
     port_lib.orc_get_env_emitter.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").POINTER(orc.Emitter)]
     _check_against_oracle(maker(), port_lib)
