@@ -23,6 +23,14 @@ HOST = PKG / "host"
 NVCC = os.environ.get("NVCC") or shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v", *os.environ.get("PB2_NVCC_EXTRA", "").split()]
+# Shading arithmetic (wavefront.cu and its known-answer twin kat.cu) is built the way the reference builds its device code
+# where that is cheap and harmless: approximate division / square root (<= 2 ulp) and flush-to-zero, three of the switches
+# its -use_fast_math implies (CMakeLists.txt:45).  Measured on B200: k_shade -8 % (Cornell) / -23 % (material grid), and
+# every parity test keeps its tolerance (profiles/README.md).  The fast transcendental substitutions (__sinf, __powf, ...)
+# are NOT taken: +1 % more, at 10x the error.  Camera rays, ray/primitive intersection and the BVH builder spell their
+# roundings out with _rn intrinsics or are built IEEE, so hit records do not depend on these flags.
+FAST_SHADING_FLAGS = ["--prec-div=false", "--prec-sqrt=false", "--ftz=true"]
+FAST_SHADING_FILES = {"wavefront.cu", "kat.cu"}
 CXX = os.environ.get("CXX") or shutil.which("g++") or "g++"
 
 
@@ -53,7 +61,8 @@ def build_pb2(force: bool = False) -> Path:
     def compile_one(src: Path):
         obj = BUILD / (src.stem + ".o")
         if force or _newer(obj, [src, *hdrs]):
-            _run([NVCC, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)], BUILD / (src.stem + ".ptxas.log"))
+            extra = FAST_SHADING_FLAGS if src.name in FAST_SHADING_FILES and "PB2_IEEE_SHADING" not in os.environ else []
+            _run([NVCC, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)], BUILD / (src.stem + ".ptxas.log"))
         return obj
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:

@@ -27,6 +27,8 @@ struct TraceCounters {
 };
 
 PB2_D uint32_t byte_of(uint32_t w, int i) { return (w >> (i * 8)) & 0xffu; }
+PB2_D void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+PB2_D void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // fixed-rounding building blocks (the CPU checker used by the tests spells out the same sequence with fmaf)
 PB2_D float ix_dot(float3 a, float3 b) { return __fmaf_rn(a.z, b.z, __fmaf_rn(a.y, b.y, __fmul_rn(a.x, b.x))); }
@@ -82,7 +84,7 @@ template<bool ANY, bool COUNT>
 PB2_D bool traverse(const SceneView &sv, float3 o, float3 d, float tmin, RayHit &hit, TraceCounters *ctr) {
     hit.prim_slot = 0xffffffffu;
     if (sv.n_nodes == 0) return false;
-    auto safe_inv = [](float x) { return 1.f / (fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); };
+    auto safe_inv = [](float x) { return __fdiv_rn(1.f, fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
     const float3 idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     // octant: bit set <=> direction component >= 0.  Children were placed so that slot ^ oct is
     // larger for nearer children; the highest set bit of the hit mask is visited first.
@@ -196,7 +198,7 @@ struct RayState {
 };
 
 PB2_D void ray_begin(RayState &r, float3 o, float3 d, float tmin, float tmax, bool empty_scene) {
-    auto safe_inv = [](float x) { return 1.f / (fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); };
+    auto safe_inv = [](float x) { return __fdiv_rn(1.f, fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
     r.o = o, r.d = d, r.tmin = tmin;
     r.idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     r.oct = (r.idir.x >= 0.f ? 4u : 0u) | (r.idir.y >= 0.f ? 2u : 0u) | (r.idir.z >= 0.f ? 1u : 0u);

@@ -23,6 +23,9 @@
 
 namespace pb2 {
 
+#ifndef PB2_SHADE_PREFETCH
+#define PB2_SHADE_PREFETCH 0 // 1: prefetch.global.L2, 2: .L1 of the next path's records — measured slower (45.6 vs 43.3 ms per Cornell step), kept for re-measurement
+#endif
 constexpr int kNumTypes = 8; // queue 0 = miss, 1..7 = EMatType
 constexpr int kCtrPerRound = 16;
 // per-round counter slots
@@ -127,11 +130,14 @@ __global__ void __launch_bounds__(256) k_generate(PathArrays pa, FrameParams fp,
         const float4 pf = make_float4((static_cast<float>(x) + jx) / static_cast<float>(fp.width),
                                       (static_cast<float>(y) + jy) / static_cast<float>(fp.height), 0.f, 1.f);
         float4 d = make_float4(dot(cam.s2c[0], pf), dot(cam.s2c[1], pf), dot(cam.s2c[2], pf), dot(cam.s2c[3], pf)); // :67
-        const float inv = 1.0f / d.w;                                                                               // :69
+        // IEEE division / square root spelled out: the primary ray must not depend on --prec-div / --prec-sqrt (a last-bit
+        // change of the direction moves silhouette pixels to another primitive)
+        const float inv = __fdiv_rn(1.0f, d.w);                                                                     // :69
         d = make_float4(d.x * inv, d.y * inv, d.z * inv, 0.f);                                                      // :70
-        const float inv_len = 1.0f / sqrtf(dot(d, d));                                                              // :71
+        const float inv_len = __fdiv_rn(1.0f, __fsqrt_rn(dot(d, d)));                                               // :71
         d = make_float4(d.x * inv_len, d.y * inv_len, d.z * inv_len, 0.f);
-        const float3 dir = normalize(mk3(dot(cam.c2w[0], d), dot(cam.c2w[1], d), dot(cam.c2w[2], d))); // :73
+        const float3 dw = mk3(dot(cam.c2w[0], d), dot(cam.c2w[1], d), dot(cam.c2w[2], d));
+        const float3 dir = dw * __fdiv_rn(1.0f, __fsqrt_rn(dot(dw, dw))); // :73 normalize
         pa.ray[2 * (size_t)p] = make_float4(cam.c2w[0].w, cam.c2w[1].w, cam.c2w[2].w, __uint_as_float(0u)); // :75-78; state = depth 0
         pa.ray[2 * (size_t)p + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
         pa.ps[2 * (size_t)p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(rng));
@@ -477,22 +483,45 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
     }
     const uint32_t total = SORTED ? start[kNumTypes] : ((counts[0] + 127u) & ~127u);
 
-    for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total; vi += gridDim.x * blockDim.x) { // total % 128 == 0: CTA-uniform
-        uint32_t emitted = 0, p = 0;
-        ShadowRay sh;
-        bool valid;
+    // queue entry of virtual index vi (SORTED: the eight material queues laid end to end, each padded to 128)
+    auto fetch = [&](uint32_t vi, uint32_t &p) -> bool {
         if (SORTED) {
             int t = 0;
 #pragma unroll
             for (int k = 1; k < kNumTypes; ++k) t += vi >= start[k] ? 1 : 0;
             const uint32_t local = vi - start[t];
-            valid = local < counts[t];
-            if (valid) p = queue[(size_t)t * capacity + local];
+            if (local >= counts[t]) return false;
+            p = queue[(size_t)t * capacity + local];
         } else {
-            valid = vi < counts[0];
-            if (valid) p = queue[vi];
+            if (vi >= counts[0]) return false;
+            p = queue[vi];
         }
+        return true;
+    };
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t p_next = 0;
+    bool valid_next = blockIdx.x * blockDim.x + threadIdx.x < total && fetch(blockIdx.x * blockDim.x + threadIdx.x, p_next);
+    for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total; vi += stride) { // total % 128 == 0: CTA-uniform
+        uint32_t emitted = 0;
+        const uint32_t p = p_next;
+        const bool valid = valid_next;
+        ShadowRay sh;
+#if PB2_SHADE_PREFETCH
+        // the next iteration's queue entry is fetched now and its three 32-byte records are requested while this path is
+        // shaded: ncu showed a third of k_shade's stall samples waiting on exactly these loads (profiles/r1c_ncu.md)
+        valid_next = vi + stride < total && fetch(vi + stride, p_next);
+        if (valid_next) {
+#if PB2_SHADE_PREFETCH == 1
+            prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.ps + 2 * (size_t)p_next);
+#else
+            prefetch_l1(pa.hit + 2 * (size_t)p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.ps + 2 * (size_t)p_next);
+#endif
+        }
+#endif
         if (valid) emitted = shade_path(sv, pa, fp, out, p, sh);
+#if !PB2_SHADE_PREFETCH
+        valid_next = vi + stride < total && fetch(vi + stride, p_next);
+#endif
         uint32_t ps, pe;
         block_append2(out.n_shadow, out.n_ext, emitted & 1u, emitted & 2u, ps, pe);
         if (emitted & 1u) { // consecutive threads write consecutive 48-byte queue entries
