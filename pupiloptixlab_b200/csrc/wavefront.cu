@@ -268,7 +268,7 @@ __device__ __forceinline__ void hit_local_geometry(const DevInstance *in, uint32
 struct ShadeOut {
     uint32_t *q_ext, *n_ext, *n_shadow;
     float *albedo, *normal, *test; // AOVs (may be null); written by the last frame of the batch only
-    uint32_t write_aov_frame;      // frame index (within the batch) whose primary hits write the AOVs; ~0u = none
+    uint32_t aov_first_slot;       // first path slot of the frame whose primary hits write the AOVs (its pixels follow); ~0u = none
 };
 
 // A shadow ray produced by shade_path; it is appended to the shadow queue by the caller (warp-aggregated).
@@ -290,8 +290,9 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
     const uint32_t sampled_type = st >> 16;
     uint32_t rng = __float_as_uint(thr4.w);
     float3 radiance = mk3(rad4);
-    const uint32_t frame = p / fp.n_pixels, pixel = p - frame * fp.n_pixels;
-    const bool write_aov = depth == 0 && frame == out.write_aov_frame;
+    // p = frame * n_pixels + pixel; only the AOV frame needs the pixel, so no per-path integer division
+    const uint32_t pixel = p - out.aov_first_slot;
+    const bool write_aov = depth == 0 && out.aov_first_slot != ~0u && pixel < fp.n_pixels;
 
     if (inst < 0) { // __miss__default, main.cu:199-215
         float3 env_radiance = mk3(0.f);
@@ -638,7 +639,8 @@ void render(Scene &s, const pb2_launch_params &lp) {
                         lp.seed_stride ? lp.seed_stride : 1u, frames };
         const unsigned grid_stream = (unsigned)std::min<uint64_t>((n_paths + 255) / 256, (uint64_t)sms * 8);
         const unsigned grid_trace = (unsigned)std::min<uint64_t>((n_paths + 127) / 128, (uint64_t)sms * 16);
-        const unsigned grid_shade = (unsigned)std::min<uint64_t>((n_paths + kNumTypes * 128 + 127) / 128, (uint64_t)sms * 12);
+        const unsigned grid_shade = (unsigned)std::min<uint64_t>((n_paths + kNumTypes * 128 + 127) / 128,
+                                                                   (uint64_t)sms * 2 * (s.shade_variant >= 4 && s.shade_variant <= 8 ? s.shade_variant : 6)); // two full waves of resident CTAs
 
         PB2_CUDA(cudaMemsetAsync(wf.counters.ptr, 0, wf.counters.bytes(), st));
         stage_begin(0);
@@ -669,14 +671,22 @@ void render(Scene &s, const pb2_launch_params &lp) {
                 ++wf.launches;
             }
             ShadeOut so{ q_out, ctr_next + CTR_EXT, ctr + CTR_SHADOW, (float *)lp.albedo_buffer, (float *)lp.normal_buffer,
-                         (float *)lp.test_buffer, last_batch ? frames - 1 : ~0u };
+                         (float *)lp.test_buffer, last_batch ? (frames - 1) * n_pixels : ~0u };
             stage_begin(2);
             if (sorted) {
-                if (s.shade_variant == 4) k_shade<4, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
-                else k_shade<6, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so);
+                switch (s.shade_variant) {
+                    case 4: k_shade<4, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so); break;
+                    case 7: k_shade<7, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so); break;
+                    case 8: k_shade<8, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so); break;
+                    default: k_shade<6, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so); break;
+                }
             } else {
-                if (s.shade_variant == 4) k_shade<4, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so);
-                else k_shade<6, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so);
+                switch (s.shade_variant) {
+                    case 4: k_shade<4, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so); break;
+                    case 7: k_shade<7, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so); break;
+                    case 8: k_shade<8, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so); break;
+                    default: k_shade<6, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so); break;
+                }
             }
             PB2_LAUNCH_CHECK();
             stage_end();
