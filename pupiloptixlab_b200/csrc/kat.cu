@@ -15,6 +15,7 @@
 #include "pt_math.cuh"
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace pb2 {
 struct KatBsdf { // mirrors LocalBsdf; slots c0..c2 as in pb2_material
@@ -25,6 +26,7 @@ struct KatBsdf { // mirrors LocalBsdf; slots c0..c2 as in pb2_material
 };
 DevTexture to_dev(const pb2_texture &t);
 DevEmitter to_dev(const pb2_emitter &e);
+std::vector<float> area_select_cdf(const DevEmitter *areas, size_t n);
 
 namespace {
 __global__ void k_rng(const uint32_t *in, uint64_t n, float *out) {
@@ -116,10 +118,10 @@ __global__ void k_emitter(const DevEmitter *em, const float *in1, const float *i
     st3(o + 8, rad);
     o[11] = pdf, o[12] = o[13] = o[14] = o[15] = 0.f;
 }
-__global__ void k_select(const DevEmitter *areas, uint32_t m, const DevEmitter *env, const float *p, uint64_t n, int32_t *out) {
+__global__ void k_select(const DevEmitter *areas, const float *cdf, uint32_t m, const DevEmitter *env, const float *p, uint64_t n, int32_t *out) {
     uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const DevEmitter *e = select_emitter(areas, m, env, p[i]);
+    const DevEmitter *e = select_emitter(areas, cdf, m, env, p[i]);
     out[i] = !e ? -1 : (e == env ? (int32_t)m : (int32_t)(e - areas));
 }
 template<typename T>
@@ -204,8 +206,10 @@ int run_kat(const char *what_c, const void *in0, const void *in1, const void *in
         e[m].type = PB2_EMIT_CONST_ENV;
         auto a = up<DevEmitter>(e.data(), m + 1);
         auto b = up<float>(in1, n);
+        const std::vector<float> cdf_h = area_select_cdf(e.data(), m);
+        auto cdf = up<float>(cdf_h.data(), m);
         DevBuf<int32_t> o(n);
-        k_select<<<g, 128>>>(a.ptr, m, has_env ? a.ptr + m : nullptr, b.ptr, n, o.ptr);
+        k_select<<<g, 128>>>(a.ptr, cdf.ptr, m, has_env ? a.ptr + m : nullptr, b.ptr, n, o.ptr);
         PB2_LAUNCH_CHECK();
         PB2_CUDA(cudaDeviceSynchronize());
         PB2_CUDA(cudaMemcpy(out, o.ptr, o.bytes(), cudaMemcpyDeviceToHost));

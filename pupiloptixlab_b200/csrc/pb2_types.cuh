@@ -82,6 +82,7 @@ struct SceneView {
     const DevMaterial *materials;
     const DevEmitter *areas;
     const DevEmitter *env; // nullptr: no environment emitter
+    const float *area_cdf; // n_areas running fp32 sums of select_probability, in table order (select_emitter)
     uint32_t n_areas;
     uint32_t n_nodes;
     uint32_t n_prims;

@@ -573,16 +573,13 @@ PB2_D float3 emitter_radiance(const DevEmitter *e, float2 uv) {
     }
     return tex_sample(&e->radiance, uv); // area, sphere and env map alike (emitter.h:54-71: no `scale` for the env map)
 }
-// EmitterGroup::SelectOneEmiiter, render/emitter.h:110-136: linear scan over the cumulative selection
-// probability in emitter order (same selection as the reference, same fp32 running sum).
-// Returns a pointer to the chosen emitter or nullptr when the scene has none.
-PB2_D const DevEmitter *select_emitter(const DevEmitter *areas, uint32_t n, const DevEmitter *env, float p) {
-    float sum_p = 0.f;
-    for (uint32_t i = 0; i < n; ++i) {
-        const float sp = __ldg(&areas[i].select_probability);
-        if (p <= sum_p + sp) return &areas[i];
-        sum_p += sp;
-    }
+// EmitterGroup::SelectOneEmiiter, render/emitter.h:110-136: the first area emitter (in table order) with
+// p <= (running fp32 sum of select probabilities up to and including it), else the environment emitter, else the last
+// area emitter.  `cdf` holds exactly those running sums (pb2_api.cu, area_select_cdf), so a binary search returns the
+// entry the reference's linear scan stops at.  Returns nullptr when the scene has no emitter.
+PB2_D const DevEmitter *select_emitter(const DevEmitter *areas, const float *cdf, uint32_t n, const DevEmitter *env, float p) {
+    const uint32_t i = first_not_less(cdf, n, p);
+    if (i < n) return &areas[i];
     if (env) return env;
     return n ? &areas[n - 1] : nullptr;
 }

@@ -29,6 +29,7 @@ struct Scene {
     DevBuf<DevInstance> d_inst;
     DevBuf<DevMaterial> d_mat;
     DevBuf<DevEmitter> d_areas, d_env;
+    DevBuf<float> d_area_cdf; // running sums of the area emitters' select probabilities (select_emitter)
     bool tables_dirty = true;
 
     DevBuf<Bvh8Node> d_nodes;

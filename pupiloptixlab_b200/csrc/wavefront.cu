@@ -364,7 +364,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
     {
         const float sel = rng_next(rng);
         const float e0 = rng_next(rng), e1 = rng_next(rng);
-        const DevEmitter *em = select_emitter(sv.areas, sv.n_areas, sv.env, sel);
+        const DevEmitter *em = select_emitter(sv.areas, sv.area_cdf, sv.n_areas, sv.env, sel);
         if (em) {
             EmitSample es;
             emitter_sample_direct(em, geo.position, geo.normal, frame_onb, make_float2(e0, e1), es);

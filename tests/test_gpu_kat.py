@@ -272,3 +272,31 @@ def test_select_emitter(ref):
         out = np.zeros(len(ps), np.int32)
         pb2.kat("select", arr, ps, np.array([3, has_env], np.uint32), len(ps), out)
         assert np.array_equal(out, ref[key])
+
+
+def test_select_emitter_large_table_matches_the_linear_scan(port_lib):
+    """a20: the device finds the entry by binary search over the same fp32 running sums — identical to the reference's
+    O(n) scan (render/emitter.h:110-136), including draws that land exactly on a running sum"""
+    rng = np.random.default_rng(5)
+    m = 3000
+    w = rng.random(m).astype(F) ** 3
+    w[rng.integers(0, m, 100)] = 0.0  # zero-probability entries must never be chosen over their successor... by either side
+    sp = (w / w.sum() * F(0.9)).astype(F)
+    ems = []
+    for i in range(m):
+        e = orc.Emitter()
+        e.type, e.weight, e.select_probability, e.area = orc.EMIT_TRI, 1.0, float(sp[i]), 1.0
+        ems.append(e)
+    oarr = (orc.Emitter * m)(*ems)
+    parr = (pb2.Emitter * m)(*[_pb2_emitter(e) for e in ems])
+    cum = np.zeros(m, F)
+    acc = F(0)
+    for i in range(m):
+        acc = F(acc + sp[i])
+        cum[i] = acc
+    ps = np.concatenate([rng.random(4000).astype(F), cum[rng.integers(0, m, 500)], np.nextafter(cum[:200], F(2)), [F(0), F(0.95), F(0.99999994)]]).astype(F)
+    for has_env in (1, 0):
+        want = np.array([port_lib.orc_select_emitter(oarr, m, has_env, float(p)) for p in ps], np.int32)
+        out = np.zeros(len(ps), np.int32)
+        pb2.kat("select", parr, ps, np.array([m, has_env], np.uint32), len(ps), out)
+        assert np.array_equal(out, want)
