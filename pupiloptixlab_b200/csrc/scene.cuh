@@ -46,7 +46,10 @@ struct Scene {
     int n_material_types = 0;   // distinct EMatType values among the instances (upload_tables)
     uint64_t paths_in_flight = 0;
     int refill_threshold = 26;
-    int shade_variant = 6;     // k_shade<MINB>: 4, 6 or 8 resident CTAs per SM // persistent traversal: refill idle lanes when fewer than this many are busy
+    int shade_variant = 6;     // k_shade<MINB>: 4, 6, 7 or 8 resident CTAs per SM
+    int coop_prims = -1;       // warp-cooperative primitive tests in the trace kernels: 1 on, 0 off, -1 auto (by scene size)
+    // auto: few lanes reach a leaf per step in deep trees (cooperation pays); in tiny scenes every lane does (it only costs)
+    bool use_coop_prims() const { return coop_prims == 1 || (coop_prims < 0 && n_prims >= 4096u); } // persistent traversal: refill idle lanes when fewer than this many are busy
 
     Wavefront *wf = nullptr;
     pb2_render_stats render_stats{};

@@ -44,6 +44,37 @@ def test_closest_hit_matches_brute_force(port_lib, n_tris, n_spheres, builder):
     assert np.allclose(gpu["u"][m], ref["u"][m], atol=2e-4) and np.allclose(gpu["v"][m], ref["v"][m], atol=2e-4)
 
 
+@pytest.mark.parametrize("coop", [0, 1])
+def test_both_primitive_test_schedules_give_the_same_hits(port_lib, coop):
+    """per-lane and warp-cooperative primitive tests (traverse.cuh) are two schedules of the same arithmetic"""
+    desc = _soup_desc(20000, 11, 16)
+    osc = orc.OracleScene(port_lib, desc)
+    s = pb2_scene_from_oracle(desc, osc)
+    s.build()
+    s.set_option("coop_prims", coop)
+    rays = random_rays(8000, 21)
+    ref, _ = osc.trace_closest(rays, brute=True)
+    gpu = s.trace_closest(rays)
+    compare_hits(gpu, ref, rays)
+    s.set_option("coop_prims", 1 - coop)
+    other = s.trace_closest(rays)
+    same = (gpu["inst"] == other["inst"]) & (gpu["prim"] == other["prim"])
+    assert np.count_nonzero(~same) <= len(rays) // 200  # exact-t ties may resolve differently
+    assert np.array_equal(gpu["t"][same], other["t"][same]) and np.array_equal(gpu["u"][same], other["u"][same])
+    rays[:, 7] = np.random.default_rng(2).uniform(0.5, 20.0, len(rays)).astype(np.float32)
+    a = s.trace_any(rays)
+    s.set_option("coop_prims", coop)
+    assert np.array_equal(a, s.trace_any(rays))
+    # tiny scene, forced cooperative: every lane holds primitives at once
+    small = scenes.cornell_box(64, 64, 8)
+    o2 = orc.OracleScene(port_lib, small)
+    s2 = pb2_scene_from_oracle(small, o2)
+    s2.build()
+    s2.set_option("coop_prims", coop)
+    r2 = o2.camera_rays(seed=5)
+    compare_hits(s2.trace_closest(r2), o2.trace_closest(r2, brute=True)[0], r2)
+
+
 def test_any_hit_matches_brute_force(port_lib):
     desc = _soup_desc(5000, 3, 4)
     osc = orc.OracleScene(port_lib, desc)

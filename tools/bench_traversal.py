@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--refill", type=str, default="", help="comma list of refill thresholds to sweep")
+    ap.add_argument("--coop", type=int, default=-1, help="warp-cooperative primitive tests: 1 on, 0 off, -1 auto")
     args = ap.parse_args()
     import torch
     from pupiloptixlab_b200 import pupil, scenes
@@ -75,6 +76,7 @@ def main():
 
     stream = torch.cuda.Stream()
     scene.set_stream(stream.cuda_stream)
+    scene.set_option("coop_prims", args.coop)
     s2c, c2w, _ = pupil.camera()
     prim = camera_rays(s2c, c2w, args.width, args.height)
 
