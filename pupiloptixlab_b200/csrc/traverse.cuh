@@ -50,7 +50,7 @@ PB2_D bool intersect_prim(const SceneView &sv, uint32_t slot, float3 o, float3 d
         const float3 pvec = ix_cross(d, e2);
         const float det = ix_dot(e1, pvec);
         if (det == 0.f) return false;
-        const float inv = __fdiv_rn(1.f, det);
+        const float inv = __frcp_rn(det); // correctly rounded 1 / det, the same value as __fdiv_rn(1.f, det) in fewer instructions
         const float3 tvec = ix_sub(o, v0);
         const float u = __fmul_rn(ix_dot(tvec, pvec), inv);
         if (u < 0.f || u > 1.f) return false;
@@ -84,7 +84,7 @@ template<bool ANY, bool COUNT>
 PB2_D bool traverse(const SceneView &sv, float3 o, float3 d, float tmin, RayHit &hit, TraceCounters *ctr) {
     hit.prim_slot = 0xffffffffu;
     if (sv.n_nodes == 0) return false;
-    auto safe_inv = [](float x) { return __fdiv_rn(1.f, fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
+    auto safe_inv = [](float x) { return __frcp_rn(fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
     const float3 idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     // octant: bit set <=> direction component >= 0.  Children were placed so that slot ^ oct is
     // larger for nearer children; the highest set bit of the hit mask is visited first.
@@ -198,7 +198,7 @@ struct RayState {
 };
 
 PB2_D void ray_begin(RayState &r, float3 o, float3 d, float tmin, float tmax, bool empty_scene) {
-    auto safe_inv = [](float x) { return __fdiv_rn(1.f, fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
+    auto safe_inv = [](float x) { return __frcp_rn(fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
     r.o = o, r.d = d, r.tmin = tmin;
     r.idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     r.oct = (r.idir.x >= 0.f ? 4u : 0u) | (r.idir.y >= 0.f ? 2u : 0u) | (r.idir.z >= 0.f ? 1u : 0u);
