@@ -21,7 +21,10 @@
 namespace pb2 {
 namespace {
 
-constexpr int kLeafMax = 3; // primitives per BVH8 leaf slot (unary count in 3 meta bits)
+#ifndef PB2_LEAF_MAX
+#define PB2_LEAF_MAX 3
+#endif
+constexpr int kLeafMax = PB2_LEAF_MAX; // primitives per BVH8 leaf slot (unary count in 3 meta bits)
 
 // ---- order-preserving float <-> int for atomicMin / atomicMax ------------------------------------------
 __device__ __forceinline__ int float_to_ordered(float f) {
