@@ -83,6 +83,48 @@ def test_env_map_and_bitmap_scene_parity(port_lib):
     assert relmse < 1e-3, relmse
 
 
+def test_edge_scenes(port_lib):
+    """no geometry, no emitters, ragged frame sizes, scene reloads through the device memory pool"""
+    # (1) nothing but a constant environment: every primary ray misses (__miss__default, main.cu:199-215)
+    desc = scenes.SceneDesc(max_depth=4, sensor=scenes.Sensor(width=37, height=19), shapes=[], env_radiance=(0.25, 0.5, 0.75))
+    pupil.load_scene(desc)
+    pupil.pass_config(frames_per_run=3)
+    pupil.run(1)
+    frame = pupil.buffer("final result")
+    assert frame.shape == (19, 37, 4) and np.allclose(frame[..., :3], (0.25, 0.5, 0.75), rtol=1e-6) and np.all(frame[..., 3] == 1.0)
+    assert pupil.render_stats().shadow_rays == 0
+    # (2) geometry but no emitter of any kind: black, finite, and the oracle agrees on every buffer
+    desc = scenes.cornell_box(33, 21, 5)
+    for sh in desc.shapes:
+        sh.emitter = None
+    pupil.load_scene(desc)
+    pupil.pass_config()
+    pupil.run(1)
+    ref = orc.OracleScene(port_lib, desc).render(1)
+    frame = pupil.buffer("final result")
+    assert np.all(frame[..., :3] == 0.0) and np.all(ref["frame"][:, :3] == 0.0)
+    assert np.array_equal(pupil.buffer("test").reshape(-1), ref["test"]) and np.array_equal(pupil.buffer("albedo").reshape(-1, 3), ref["albedo"])
+    # (3) ragged frame (neither side a multiple of the warp or the CTA), several batches of an odd number of frames
+    desc = scenes.cornell_box(61, 43, 8)
+    pupil.load_scene(desc)
+    pupil.scene_handle().set_option("paths_in_flight", 61 * 43 * 3)
+    pupil.pass_config(frames_per_run=7)
+    pupil.run(1)
+    first = pupil.buffer("pt accum buffer").copy()
+    ref = orc.OracleScene(port_lib, desc).render(7)
+    ok = _match(first, ref["accum"])
+    assert ok.mean() >= 0.995, ok.mean()
+    # (4) reload other scenes (device blocks go back to the pool and are reused), then the same scene again: same image
+    pupil.load_scene(scenes.material_grid(80, 45, 6))
+    pupil.pass_config(frames_per_run=2)
+    pupil.run(1)
+    pupil.load_scene(desc)
+    pupil.scene_handle().set_option("paths_in_flight", 61 * 43 * 3)
+    pupil.pass_config(frames_per_run=7)
+    pupil.run(1)
+    assert np.array_equal(pupil.buffer("pt accum buffer"), first)
+
+
 def test_progressive_running_mean_and_batching(port_lib):
     """8 x OnRun(1 frame) == 1 x OnRun(8 frames) bit for bit (main.cu:190-196 running mean in frame order), and both
     follow the oracle's 8-frame accumulation"""
