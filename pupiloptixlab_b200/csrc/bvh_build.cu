@@ -219,7 +219,7 @@ struct CollapseCtx {
     const uint32_t *sorted;
     const float4 *box_lo, *box_hi;
     const PrimRec *prims_in;
-    PrimRec *prims_out;
+    uint32_t *dst_of_sorted; // leaf-order slot of the primitive at each sorted position
     Bvh8Node *nodes;
     uint32_t *counters; // [0] nodes allocated, [1] prims allocated, [2] next-level queue size, [3] max depth
     float *sah;         // [0] accumulated SAH cost (un-normalised)
@@ -244,10 +244,25 @@ __device__ __forceinline__ Ref load_ref(const CollapseCtx &c, int ref) {
     }
     return r;
 }
+// primitive records into BVH leaf order: prims_out[dst_of_sorted[i]] = prims_in[sorted[i]]
+__global__ void __launch_bounds__(256) k_scatter_prims(const PrimRec *__restrict__ prims_in, const uint32_t *__restrict__ sorted,
+                                                        const uint32_t *__restrict__ dst_of_sorted, uint32_t n, PrimRec *__restrict__ prims_out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 *src = reinterpret_cast<const float4 *>(prims_in + sorted[i]);
+        float4 *dst = reinterpret_cast<float4 *>(prims_out + dst_of_sorted[i]);
+        const float4 a = __ldg(src), b = __ldg(src + 1), cc = __ldg(src + 2);
+        dst[0] = a, dst[1] = b, dst[2] = cc;
+    }
+}
 // work item: x = wide node index, y = binary ref, z = depth
-__global__ void k_collapse(CollapseCtx c, const uint4 *__restrict__ q_in, uint32_t n_in, uint4 *__restrict__ q_out) {
+#ifndef PB2_COLLAPSE_MINB
+#define PB2_COLLAPSE_MINB 6
+#endif
+__global__ void __launch_bounds__(128, PB2_COLLAPSE_MINB) k_collapse(CollapseCtx c, const uint4 *__restrict__ q_in, uint32_t n_in, uint4 *__restrict__ q_out) {
     const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, w < n_in); // a prefix of the warp: work items are dense
     if (w >= n_in) return;
+    const uint32_t lane = threadIdx.x & 31u;
     const uint4 item = q_in[w];
     const Ref self = load_ref(c, (int)item.y);
     Ref ch[8];
@@ -280,35 +295,61 @@ __global__ void k_collapse(CollapseCtx c, const uint4 *__restrict__ q_in, uint32
         else n_leaf_prims += ch[i].count;
     }
     // ---- octant slot assignment (greedy on dot(centroid offset, octant direction)) ----
+    // Same greedy order as a plain triple loop (children ascending, slots ascending, first maximum wins); the centroid
+    // offsets are hoisted and the bookkeeping lives in bit masks so the 8 x 8 inner loops unroll into registers
+    // (ncu: the loop was 40 % of the kernel's instructions, most of them local-memory traffic).
     const float3 centre = (self.lo + self.hi) * 0.5f;
-    int slot_of[8];
-    bool slot_used[8] = { false, false, false, false, false, false, false, false };
-    bool done[8] = { false, false, false, false, false, false, false, false };
+    float offx[8], offy[8], offz[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float3 off = i < n ? (ch[i].lo + ch[i].hi) * 0.5f - centre : mk3(0.f);
+        offx[i] = off.x, offy[i] = off.y, offz[i] = off.z;
+    }
+    uint32_t slot_of_packed = 0, slot_used = 0, done = 0; // 4 bits per child | bit per slot | bit per child
     for (int round = 0; round < n; ++round) {
         float best = -FLT_MAX;
-        int bi = -1, bs = -1;
-        for (int i = 0; i < n; ++i) {
-            if (done[i]) continue;
-            const float3 off = (ch[i].lo + ch[i].hi) * 0.5f - centre;
-            for (int s = 0; s < 8; ++s) {
-                if (slot_used[s]) continue;
-                const float cost = ((s & 4) ? off.x : -off.x) + ((s & 2) ? off.y : -off.y) + ((s & 1) ? off.z : -off.z);
-                if (cost > best) best = cost, bi = i, bs = s;
+        int bi = 0, bs = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i >= n || (done >> i & 1u)) continue;
+#pragma unroll
+            for (int sl = 0; sl < 8; ++sl) {
+                if (slot_used >> sl & 1u) continue;
+                const float cost = ((sl & 4) ? offx[i] : -offx[i]) + ((sl & 2) ? offy[i] : -offy[i]) + ((sl & 1) ? offz[i] : -offz[i]);
+                if (cost > best) best = cost, bi = i, bs = sl;
             }
         }
-        slot_of[bi] = bs, slot_used[bs] = true, done[bi] = true;
+        slot_of_packed |= (uint32_t)bs << (4 * bi), slot_used |= 1u << bs, done |= 1u << bi;
     }
     int child_in_slot[8];
-    for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
-    for (int i = 0; i < n; ++i) child_in_slot[slot_of[i]] = i;
+#pragma unroll
+    for (int sl = 0; sl < 8; ++sl) child_in_slot[sl] = -1;
+    for (int i = 0; i < n; ++i) child_in_slot[(slot_of_packed >> (4 * i)) & 7u] = i;
 
     // ---- allocate children / primitive range ----
-    uint32_t child_base = 0, prim_base = 0;
-    if (n_inner) child_base = atomicAdd(&c.counters[0], (uint32_t)n_inner);
-    if (n_leaf_prims) prim_base = atomicAdd(&c.counters[1], (uint32_t)n_leaf_prims);
-    uint32_t q_base = 0;
-    if (n_inner) q_base = atomicAdd(&c.counters[2], (uint32_t)n_inner);
-    atomicMax(&c.counters[3], item.z + 1);
+    // One atomic per warp and counter instead of four per thread: millions of threads adding to the same three words
+    // serialise in L2 (the per-thread version spent most of the kernel's 10 ms per 30 M triangles there).
+    uint32_t child_base = 0, prim_base = 0, q_base = 0;
+    {
+        __syncwarp(warp_mask);
+        uint32_t in_incl = (uint32_t)n_inner, pr_incl = (uint32_t)n_leaf_prims;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(warp_mask, in_incl, d), b = __shfl_up_sync(warp_mask, pr_incl, d);
+            if ((int)lane >= d) in_incl += a, pr_incl += b;
+        }
+        const int last = 31 - __clz(warp_mask);
+        const uint32_t total_in = __shfl_sync(warp_mask, in_incl, last), total_pr = __shfl_sync(warp_mask, pr_incl, last);
+        uint32_t b0 = 0, b1 = 0, b2 = 0;
+        if (lane == 0) {
+            if (total_in) b0 = atomicAdd(&c.counters[0], total_in), b2 = atomicAdd(&c.counters[2], total_in);
+            if (total_pr) b1 = atomicAdd(&c.counters[1], total_pr);
+            atomicMax(&c.counters[3], item.z + 1);
+        }
+        b0 = __shfl_sync(warp_mask, b0, 0), b1 = __shfl_sync(warp_mask, b1, 0), b2 = __shfl_sync(warp_mask, b2, 0);
+        child_base = b0 + in_incl - (uint32_t)n_inner, q_base = b2 + in_incl - (uint32_t)n_inner;
+        prim_base = b1 + pr_incl - (uint32_t)n_leaf_prims;
+    }
 
     // ---- quantisation frame ----
     const float3 ext = self.hi - self.lo;
@@ -320,6 +361,9 @@ __global__ void k_collapse(CollapseCtx c, const uint4 *__restrict__ q_in, uint32
     };
     const int ex = exp_of(ext.x), ey = exp_of(ext.y), ez = exp_of(ext.z);
     const float sx = __int_as_float((ex + 127) << 23), sy = __int_as_float((ey + 127) << 23), sz = __int_as_float((ez + 127) << 23);
+    // 1 / scale is a power of two as well: multiplying by it gives the same value as the division (both exact scalings)
+    auto inv_pow2 = [](int e, float scale) { return e <= 126 ? __int_as_float((127 - e) << 23) : 1.f / scale; };
+    const float isx = inv_pow2(ex, sx), isy = inv_pow2(ey, sy), isz = inv_pow2(ez, sz);
     const float3 p = self.lo;
 
     uint32_t imask = 0, meta[8], qlo[3][8], qhi[3][8];
@@ -333,20 +377,20 @@ __global__ void k_collapse(CollapseCtx c, const uint4 *__restrict__ q_in, uint32
             continue;
         }
         const Ref &r = ch[i];
-        auto qfloor = [](float v, float org, float scale) -> uint32_t {
-            float q = floorf((v - org) / scale);
+        auto qfloor = [](float v, float org, float scale, float inv_scale) -> uint32_t {
+            float q = floorf((v - org) * inv_scale);
             q = fminf(fmaxf(q, 0.f), 255.f);
             if (q > 0.f && org + q * scale > v) q -= 1.f; // rounding of (v - org) must not shrink the box
             return (uint32_t)q;
         };
-        auto qceil = [](float v, float org, float scale) -> uint32_t {
-            float q = ceilf((v - org) / scale);
+        auto qceil = [](float v, float org, float scale, float inv_scale) -> uint32_t {
+            float q = ceilf((v - org) * inv_scale);
             q = fminf(fmaxf(q, 0.f), 255.f);
             if (q < 255.f && org + q * scale < v) q += 1.f;
             return (uint32_t)q;
         };
-        qlo[0][s] = qfloor(r.lo.x, p.x, sx), qlo[1][s] = qfloor(r.lo.y, p.y, sy), qlo[2][s] = qfloor(r.lo.z, p.z, sz);
-        qhi[0][s] = qceil(r.hi.x, p.x, sx), qhi[1][s] = qceil(r.hi.y, p.y, sy), qhi[2][s] = qceil(r.hi.z, p.z, sz);
+        qlo[0][s] = qfloor(r.lo.x, p.x, sx, isx), qlo[1][s] = qfloor(r.lo.y, p.y, sy, isy), qlo[2][s] = qfloor(r.lo.z, p.z, sz, isz);
+        qhi[0][s] = qceil(r.hi.x, p.x, sx, isx), qhi[1][s] = qceil(r.hi.y, p.y, sy, isy), qhi[2][s] = qceil(r.hi.z, p.z, sz, isz);
         if (r.count > kLeafMax) {
             imask |= 1u << s;
             meta[s] = (1u << 5) | (24u + s);
@@ -355,7 +399,9 @@ __global__ void k_collapse(CollapseCtx c, const uint4 *__restrict__ q_in, uint32
         } else {
             const uint32_t unary = r.count == 1 ? 1u : r.count == 2 ? 3u : 7u;
             meta[s] = (unary << 5) | prim_off;
-            for (int k = 0; k < r.count; ++k) c.prims_out[prim_base + prim_off + k] = c.prims_in[c.sorted[r.first + k]];
+            // the 48-byte records are moved by k_scatter_prims afterwards (one thread per record instead of a dependent
+            // gather loop per wide node: the loop was the kernel's largest single stall)
+            for (int k = 0; k < r.count; ++k) c.dst_of_sorted[r.first + k] = prim_base + prim_off + k;
             prim_off += r.count;
             sah_local += half_area(r.lo, r.hi) * r.count;
         }
@@ -369,7 +415,13 @@ __global__ void k_collapse(CollapseCtx c, const uint4 *__restrict__ q_in, uint32
     node.n3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
     node.n4 = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
     c.nodes[item.x] = node;
-    atomicAdd(c.sah, sah_local);
+    __syncwarp(warp_mask);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        const float other = __shfl_down_sync(warp_mask, sah_local, d);
+        if (lane + d < 32u && (warp_mask >> (lane + d) & 1u)) sah_local += other;
+    }
+    if (lane == 0) atomicAdd(c.sah, sah_local);
 }
 }// namespace
 
@@ -463,7 +515,8 @@ void build_bvh(Scene &s) {
     DevBuf<uint4> qa(n), qb(n);
     uint4 root = make_uint4(0u, n > 1 ? 0u : (uint32_t)~0, 0u, 0u); // n == 1: leaf ref ~0
     PB2_CUDA(cudaMemcpyAsync(qa.ptr, &root, sizeof root, cudaMemcpyHostToDevice, st));
-    CollapseCtx cc{ t, sorted.ptr, box_lo.ptr, box_hi.ptr, prims_in.ptr, s.d_prims.ptr, nodes.ptr, counters.ptr, sah.ptr };
+    DevBuf<uint32_t> dst_of_sorted(n);
+    CollapseCtx cc{ t, sorted.ptr, box_lo.ptr, box_hi.ptr, prims_in.ptr, dst_of_sorted.ptr, nodes.ptr, counters.ptr, sah.ptr };
     uint32_t n_in = 1;
     uint4 *q_in = qa.ptr, *q_out = qb.ptr;
     uint32_t host_counters[4];
@@ -478,6 +531,13 @@ void build_bvh(Scene &s) {
     }
     s.n_nodes = host_counters[0], s.n_prims = host_counters[1];
     if (s.n_prims != n) throw std::runtime_error("pb2_bvh_build: collapse lost primitives");
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        k_scatter_prims<<<(unsigned)std::min<uint64_t>(div_up(n, 256), (uint64_t)sms * 8), 256, 0, st>>>(prims_in.ptr, sorted.ptr, dst_of_sorted.ptr, n, s.d_prims.ptr);
+        PB2_LAUNCH_CHECK();
+    }
     // shrink the node array to its final size
     s.d_nodes.alloc(s.n_nodes);
     PB2_CUDA(cudaMemcpyAsync(s.d_nodes.ptr, nodes.ptr, s.n_nodes * sizeof(Bvh8Node), cudaMemcpyDeviceToDevice, st));
