@@ -544,6 +544,7 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     else if (n == "sort_by_material") s.sort_by_material = value < 0 ? -1 : (value != 0);
     else if (n == "refill_threshold") s.refill_threshold = (int)std::min<int64_t>(33, std::max<int64_t>(0, value));
     else if (n == "shade_variant") s.shade_variant = (int)value;
+    else if (n == "two_lanes") s.two_lanes = value != 0;
     else if (n == "coop_prims") s.coop_prims = (int)std::min<int64_t>(1, std::max<int64_t>(-1, value));
     else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);
     else return fail(PB2_ERR_ARG, "pb2_scene_set_option: unknown option " + n);

@@ -47,6 +47,11 @@ struct Scene {
     uint64_t paths_in_flight = 0;
     int refill_threshold = 26;
     int shade_variant = 6;     // k_shade<MINB>: 4, 6, 7 or 8 resident CTAs per SM
+    // two batches in flight on two streams, the second one kernel late, so that one batch's HBM-bound shade kernel meets the
+    // other's issue-bound trace kernels.  Measured +1.9 % (Cornell), +5.4 % (material grid), +1.5 % (terrain): k_shade alone
+    // fills the register file, so the kernels mostly time-share the SMs instead of co-residing.  Off by default: with it a
+    // kernel's event duration includes the time it shares the GPU, which would blur the per-kernel numbers bench.py reports.
+    bool two_lanes = false;
     int coop_prims = -1;       // warp-cooperative primitive tests in the trace kernels: 1 on, 0 off, -1 auto (by scene size)
     // auto: few lanes reach a leaf per step in deep trees (cooperation pays); in tiny scenes every lane does (it only costs)
     bool use_coop_prims() const { return coop_prims == 1 || (coop_prims < 0 && n_prims >= 4096u); } // persistent traversal: refill idle lanes when fewer than this many are busy

@@ -31,23 +31,17 @@ constexpr int kCtrPerRound = 16;
 // per-round counter slots
 enum { CTR_EXT = 0, CTR_SHADOW = 1, CTR_MAT0 = 2 /* ..9 */, CTR_WORK_EXT = 10, CTR_WORK_SHADOW = 11 };
 
-struct Wavefront {
+// Path state of one batch in flight.  A render call keeps two of them going on two streams ("lanes") so that the
+// HBM-bound shade kernel of one batch runs next to the issue-bound trace kernels of the other (profiles/README.md).
+struct Lane {
     uint64_t capacity = 0;
     DevBuf<float4> ray, hit, ps, shq; // 32-byte records per path slot (ray, hit, ps) and 48-byte shadow-queue entries (shq)
     DevBuf<uint32_t> q_ext[2], q_mat;
     DevBuf<uint32_t> counters; // (max_depth + 2) rounds x kCtrPerRound
-    DevBuf<unsigned long long> trav_counters, ray_totals;
     uint32_t rounds_alloc = 0;
-    struct Ev {
-        int stage;
-        cudaEvent_t a, b;
-    };
-    std::vector<Ev> events;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    uint64_t launches = 0;
-    uint32_t rounds_used = 0, batches = 0, n_extend = 0, n_shade = 0, n_shadow = 0;
-    bool stats_pending = false, sorted = false;
-
+    cudaStream_t stream = nullptr;      // lane 0: the scene's stream; lane 1: `own`
+    cudaStream_t own = nullptr;
+    cudaEvent_t accumulated = nullptr;  // recorded after the lane's k_accumulate: batches fold into the image in frame order
     void ensure(uint64_t paths, uint32_t rounds) {
         if (paths > capacity) {
             capacity = paths;
@@ -58,15 +52,40 @@ struct Wavefront {
             rounds_alloc = rounds;
             counters.alloc((size_t)rounds * kCtrPerRound);
         }
+        if (!accumulated) PB2_CUDA(cudaEventCreateWithFlags(&accumulated, cudaEventDisableTiming));
+    }
+    ~Lane() {
+        if (accumulated) cudaEventDestroy(accumulated);
+        if (own) cudaStreamDestroy(own);
+    }
+};
+struct Wavefront {
+    Lane lane[2];
+    DevBuf<unsigned long long> trav_counters, ray_totals;
+    struct Ev {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<Ev> events;
+    cudaEvent_t t0 = nullptr, t1 = nullptr, fork = nullptr, stagger = nullptr, join = nullptr;
+    uint64_t launches = 0;
+    uint32_t rounds_used = 0, batches = 0, n_extend = 0, n_shade = 0, n_shadow = 0, lanes_used = 1;
+    bool stats_pending = false, sorted = false;
+
+    void ensure() {
         if (!trav_counters.ptr) trav_counters.alloc(8), ray_totals.alloc(2);
         if (!t0) {
             PB2_CUDA(cudaEventCreate(&t0));
             PB2_CUDA(cudaEventCreate(&t1));
+            PB2_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+            PB2_CUDA(cudaEventCreateWithFlags(&stagger, cudaEventDisableTiming));
+            PB2_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+            PB2_CUDA(cudaStreamCreateWithFlags(&lane[1].own, cudaStreamNonBlocking));
         }
     }
     ~Wavefront() {
         for (auto &e : events) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
-        if (t0) cudaEventDestroy(t0), cudaEventDestroy(t1);
+        if (t0) cudaEventDestroy(t0), cudaEventDestroy(t1), cudaEventDestroy(fork), cudaEventDestroy(stagger), cudaEventDestroy(join);
     }
 };
 void wavefront_destroy(Wavefront *wf) { delete wf; }
@@ -542,7 +561,7 @@ __global__ void k_collect_counts(const uint32_t *__restrict__ counters, uint32_t
         if (r + 1 < rounds) sh += counters[r * kCtrPerRound + CTR_SHADOW];
     }
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o), sh += __shfl_xor_sync(0xffffffffu, sh, o);
-    if (threadIdx.x == 0) totals[0] += c, totals[1] += sh;
+    if (threadIdx.x == 0) atomicAdd(&totals[0], c), atomicAdd(&totals[1], sh); // two lanes may finish a batch at the same time
 }
 
 // ---- accumulate: main.cu:190-196 ---------------------------------------------------------------------------
@@ -592,18 +611,20 @@ void render(Scene &s, const pb2_launch_params &lp) {
     s.upload_tables();
     if (!s.wf) s.wf = new Wavefront();
     Wavefront &wf = *s.wf;
-    cudaStream_t st = s.stream;
+    wf.ensure();
 
     const uint32_t n_pixels = lp.width * lp.height;
     const uint32_t n_frames = std::max(1u, lp.n_frames);
-    // paths in flight per batch: measured on the Cornell box at 1080p (profiles/README.md) 2 Mi -> 927, 4 Mi -> 1054, 16 Mi ->
-    // 1202, 32 Mi -> 1226, 64 Mi -> 1239 Msamples/s (later bounces leave short queues; bigger batches amortise their
-    // launch gaps and tails).  32 Mi paths = 4.7 GB of path state out of 180 GB.
+    // paths in flight: measured on the Cornell box at 1080p (profiles/README.md) 2 Mi -> 927, 4 Mi -> 1054, 16 Mi -> 1202,
+    // 32 Mi -> 1226, 64 Mi -> 1239 Msamples/s with one batch in flight (later bounces leave short queues; bigger batches
+    // amortise their launch gaps and tails).  32 Mi paths = 4.7 GB of path state out of 180 GB, shared by the two lanes.
     const uint64_t target = s.paths_in_flight ? s.paths_in_flight : (32ull << 20);
-    const uint32_t S = (uint32_t)std::min<uint64_t>(n_frames, std::max<uint64_t>(1, target / n_pixels));
+    const uint32_t n_lanes = (s.two_lanes && n_frames >= 2) ? 2u : 1u;
+    const uint32_t S = (uint32_t)std::min<uint64_t>((n_frames + n_lanes - 1) / n_lanes, std::max<uint64_t>(1, target / n_lanes / n_pixels));
     const uint32_t rounds = std::max(1u, lp.max_depth);
-    wf.ensure((uint64_t)S * n_pixels, rounds + 1);
     if ((uint64_t)S * n_pixels >= 0xffffffffull) throw std::runtime_error("pb2_render: too many paths in flight");
+    wf.lane[0].stream = s.stream, wf.lane[1].stream = wf.lane[1].own;
+    for (uint32_t l = 0; l < n_lanes; ++l) wf.lane[l].ensure((uint64_t)S * n_pixels, rounds + 1);
 
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -612,12 +633,12 @@ void render(Scene &s, const pb2_launch_params &lp) {
     const bool coop = s.use_coop_prims();
     // material sorting pays when shading diverges: on by default only for scenes with more than one material type
     const bool sorted = s.sort_by_material == 1 || (s.sort_by_material < 0 && s.n_material_types > 1);
-    PathArrays pa{ wf.ray.ptr, wf.hit.ptr, wf.ps.ptr, wf.shq.ptr };
-    wf.sorted = sorted;
+    wf.sorted = sorted, wf.lanes_used = n_lanes;
 
     for (auto &e : wf.events) cudaEventDestroy(e.a), cudaEventDestroy(e.b);
     wf.events.clear();
     wf.launches = 0, wf.batches = 0, wf.rounds_used = rounds, wf.n_extend = wf.n_shade = wf.n_shadow = 0;
+    cudaStream_t st = s.stream; // stream of the batch being issued
     auto stage_begin = [&](int stage) {
         if (!s.profiling) return;
         Wavefront::Ev e{ stage, nullptr, nullptr };
@@ -628,12 +649,20 @@ void render(Scene &s, const pb2_launch_params &lp) {
     auto stage_end = [&]() {
         if (s.profiling) cudaEventRecord(wf.events.back().b, st);
     };
-    if (s.counting) wf.trav_counters.zero(st);
-    wf.ray_totals.zero(st);
-    PB2_CUDA(cudaEventRecord(wf.t0, st));
+    if (s.counting) wf.trav_counters.zero(s.stream);
+    wf.ray_totals.zero(s.stream);
+    PB2_CUDA(cudaEventRecord(wf.t0, s.stream));
+    if (n_lanes == 2) { // lane 1 starts after everything already queued on the scene's stream
+        PB2_CUDA(cudaEventRecord(wf.fork, s.stream));
+        PB2_CUDA(cudaStreamWaitEvent(wf.lane[1].stream, wf.fork, 0));
+    }
 
     uint32_t sample_cnt = lp.sample_cnt;
-    for (uint32_t f0 = 0; f0 < n_frames; f0 += S) {
+    uint32_t batch = 0;
+    for (uint32_t f0 = 0; f0 < n_frames; f0 += S, ++batch) {
+        Lane &ln = wf.lane[batch % n_lanes];
+        st = ln.stream;
+        PathArrays pa{ ln.ray.ptr, ln.hit.ptr, ln.ps.ptr, ln.shq.ptr };
         const uint32_t frames = std::min(S, n_frames - f0);
         const uint32_t n_paths = frames * n_pixels;
         FrameParams fp{ lp.width, lp.height, n_pixels, lp.max_depth, lp.random_seed + f0 * (lp.seed_stride ? lp.seed_stride : 1u),
@@ -643,29 +672,33 @@ void render(Scene &s, const pb2_launch_params &lp) {
         const unsigned grid_shade = (unsigned)std::min<uint64_t>((n_paths + kNumTypes * 128 + 127) / 128,
                                                                    (uint64_t)sms * 2 * (s.shade_variant >= 4 && s.shade_variant <= 8 ? s.shade_variant : 6)); // two full waves of resident CTAs
 
-        PB2_CUDA(cudaMemsetAsync(wf.counters.ptr, 0, wf.counters.bytes(), st));
+        // the second lane starts one kernel late, so that its trace kernels meet the first lane's shade kernels rather
+        // than both lanes running the same stage side by side
+        if (batch == 1 && n_lanes == 2) PB2_CUDA(cudaStreamWaitEvent(st, wf.stagger, 0));
+        PB2_CUDA(cudaMemsetAsync(ln.counters.ptr, 0, ln.counters.bytes(), st));
         stage_begin(0);
-        k_generate<<<grid_stream, 256, 0, st>>>(pa, fp, s.cam, wf.q_ext[0].ptr, n_paths);
+        k_generate<<<grid_stream, 256, 0, st>>>(pa, fp, s.cam, ln.q_ext[0].ptr, n_paths);
         PB2_LAUNCH_CHECK();
         stage_end();
-        PB2_CUDA(cudaMemcpyAsync(wf.counters.ptr + CTR_EXT, &n_paths, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        PB2_CUDA(cudaMemcpyAsync(ln.counters.ptr + CTR_EXT, &n_paths, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         ++wf.launches;
 
         const bool last_batch = f0 + frames >= n_frames;
         for (uint32_t r = 0; r < rounds; ++r) {
-            uint32_t *ctr = wf.counters.ptr + (size_t)r * kCtrPerRound, *ctr_next = ctr + kCtrPerRound;
-            uint32_t *q_in = wf.q_ext[r & 1].ptr, *q_out = wf.q_ext[(r + 1) & 1].ptr;
+            uint32_t *ctr = ln.counters.ptr + (size_t)r * kCtrPerRound, *ctr_next = ctr + kCtrPerRound;
+            uint32_t *q_in = ln.q_ext[r & 1].ptr, *q_out = ln.q_ext[(r + 1) & 1].ptr;
             stage_begin(1);
             {
                 auto k = s.counting ? (coop ? k_extend<true, true> : k_extend<true, false>) : (coop ? k_extend<false, true> : k_extend<false, false>);
-                k<<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, sorted ? 1 : 0,
+                k<<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, sorted ? 1 : 0,
                                               ctr + CTR_WORK_EXT, s.counting ? wf.trav_counters.ptr : nullptr, s.refill_threshold);
             }
             PB2_LAUNCH_CHECK();
             stage_end();
+            if (batch == 0 && r == 0 && n_lanes == 2) PB2_CUDA(cudaEventRecord(wf.stagger, st));
             if (sorted) {
                 stage_begin(2);
-                k_bin<<<grid_stream, 256, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity);
+                k_bin<<<grid_stream, 256, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity);
                 PB2_LAUNCH_CHECK();
                 stage_end();
                 ++wf.launches;
@@ -675,17 +708,17 @@ void render(Scene &s, const pb2_launch_params &lp) {
             stage_begin(2);
             if (sorted) {
                 switch (s.shade_variant) {
-                    case 4: k_shade<4, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so); break;
-                    case 7: k_shade<7, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so); break;
-                    case 8: k_shade<8, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so); break;
-                    default: k_shade<6, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, wf.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)wf.capacity, so); break;
+                    case 4: k_shade<4, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
+                    case 7: k_shade<7, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
+                    case 8: k_shade<8, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
+                    default: k_shade<6, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
                 }
             } else {
                 switch (s.shade_variant) {
-                    case 4: k_shade<4, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so); break;
-                    case 7: k_shade<7, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so); break;
-                    case 8: k_shade<8, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so); break;
-                    default: k_shade<6, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)wf.capacity, so); break;
+                    case 4: k_shade<4, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
+                    case 7: k_shade<7, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
+                    case 8: k_shade<8, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
+                    default: k_shade<6, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
                 }
             }
             PB2_LAUNCH_CHECK();
@@ -700,19 +733,27 @@ void render(Scene &s, const pb2_launch_params &lp) {
                 ++wf.launches, ++wf.n_shadow;
             }
         }
+        // batches fold into the image in frame order (the running mean of main.cu:190-196 depends on it): wait for the
+        // previous batch's accumulate, which ran on the other lane
+        if (batch > 0 && n_lanes == 2) PB2_CUDA(cudaStreamWaitEvent(st, wf.lane[(batch - 1) % n_lanes].accumulated, 0));
         stage_begin(4);
         k_accumulate<<<(unsigned)std::min<uint64_t>((n_pixels + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>(
-            wf.ps.ptr, n_pixels, frames, lp.accumulate, sample_cnt, (float4 *)lp.accum_buffer, (float4 *)lp.frame_buffer);
+            ln.ps.ptr, n_pixels, frames, lp.accumulate, sample_cnt, (float4 *)lp.accum_buffer, (float4 *)lp.frame_buffer);
         PB2_LAUNCH_CHECK();
         stage_end();
+        if (n_lanes == 2) PB2_CUDA(cudaEventRecord(ln.accumulated, st));
         ++wf.launches;
         if (lp.accumulate == 1) sample_cnt += frames;
-        k_collect_counts<<<1, 32, 0, st>>>(wf.counters.ptr, rounds, wf.ray_totals.ptr);
+        k_collect_counts<<<1, 32, 0, st>>>(ln.counters.ptr, rounds, wf.ray_totals.ptr);
         PB2_LAUNCH_CHECK();
         ++wf.launches;
         ++wf.batches;
     }
-    PB2_CUDA(cudaEventRecord(wf.t1, st));
+    if (n_lanes == 2) { // the scene's stream continues after both lanes
+        PB2_CUDA(cudaEventRecord(wf.join, wf.lane[1].stream));
+        PB2_CUDA(cudaStreamWaitEvent(s.stream, wf.join, 0));
+    }
+    PB2_CUDA(cudaEventRecord(wf.t1, s.stream));
     wf.stats_pending = true;
 }
 

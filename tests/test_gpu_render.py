@@ -149,6 +149,21 @@ def test_progressive_running_mean_and_batching(port_lib):
     s.set_option("paths_in_flight", 0)
 
 
+def test_two_batches_in_flight_give_the_same_image():
+    """`two_lanes`: batches alternate between two streams but still fold into the running mean in frame order"""
+    desc = scenes.material_grid(96, 54, 6)
+    out = []
+    for lanes in (0, 1):
+        pupil.load_scene(desc)
+        sc = pupil.scene_handle()
+        sc.set_option("two_lanes", lanes)
+        sc.set_option("paths_in_flight", 96 * 54 * 4)
+        pupil.pass_config(frames_per_run=11)
+        pupil.run(2)
+        out.append((pupil.buffer("pt accum buffer").copy(), pupil.buffer("albedo").copy(), pupil.render_stats().closest_rays))
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+
+
 def test_accumulate_off_overwrites(port_lib):
     desc = scenes.cornell_box(48, 48, 5)
     pupil.load_scene(desc)
