@@ -178,6 +178,11 @@ def buffer(name: str) -> np.ndarray:
     return out
 
 
+def buffer_into(name: str, host_ptr: int, nbytes: int):
+    """Download a named buffer into caller-owned host memory (pinned memory makes the copy a straight DMA)."""
+    check(lib().pupil_buffer_download(name.encode(), C.c_void_p(host_ptr), nbytes))
+
+
 def film():
     w, h, d = u32(), u32(), u32()
     check(lib().pupil_get_film(C.byref(w), C.byref(h), C.byref(d)))
