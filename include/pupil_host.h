@@ -61,13 +61,18 @@ int pupil_get_instance(uint32_t index, float xform[16], pb2_material *material, 
  * <string name="filename"> says; rgba = width*height float4 texels, row 0 = first row of the picture (copied) */
 int pupil_register_image(const char *key, const float *rgba, uint32_t width, uint32_t height);
 /* util::BitmapTexture::Load / Save (framework/util/texture.cpp:87-174, :13-85) on their own: hdr, exr, png, pfm in;
- * format 0 = hdr, 1 = exr, 2 = pfm out (rgba: row 0 = bottom of the picture, as in the frame buffers) */
+ * format 0 = hdr, 1 = exr, 2 = pfm, 3 = png as the reference's canvas shows the buffer (gamma 2.2; system/gui/output.hlsl:30-72,
+ * gui.cpp:60-61), 4 = png with ACES tone mapping as well, out (rgba: row 0 = bottom of the picture, as in the frame buffers) */
 int pupil_image_load(const char *path, uint32_t *width, uint32_t *height, float *rgba, uint64_t capacity_in_floats);
 int pupil_image_save(const char *path, const float *rgba, uint32_t width, uint32_t height, int format);
 /* saves a named device buffer of the current scene (float4 buffers only), e.g. "final result" */
 int pupil_save_buffer(const char *name, const char *path, int format);
 /* EmitterHelper's env-map tables (world/emitter.cpp:107-149): pass NULL arrays to query the sizes */
 int pupil_get_env_tables(uint32_t *map_w, uint32_t *map_h, float *row_cdf, float *row_weight, float *col_cdf);
+/* RenderObject::UpdateTransform (framework/world/render_object.cpp:72-80) on the index-th render object: row-major 4x4
+ * object-to-world matrix.  Its area emitters are rebuilt (EmitterHelper::ResetAreaEmitter), the acceleration structure is
+ * rebuilt on the next run and the pass restarts its accumulation, as after IAS::Update in the reference. */
+int pupil_set_instance_transform(uint32_t index, const float xform[16]);
 int pupil_num_area_emitters(void);
 int pupil_get_emitters(pb2_emitter *areas, pb2_emitter *env, int32_t *has_env);
 /* World::GetSceneHandle(): the pb2 scene (BVH built, camera and emitters uploaded) for pb2_trace_* etc. */

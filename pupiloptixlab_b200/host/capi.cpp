@@ -94,16 +94,19 @@ int pupil_image_load(const char *path, uint32_t *width, uint32_t *height, float 
     return 0;
 }
 int pupil_image_save(const char *path, const float *rgba, uint32_t width, uint32_t height, int format) {
-    if (!path || format < 0 || format > 2) return Fail("pupil_image_save: bad arguments");
-    return util::SaveImage(rgba, width, height, path, static_cast<util::EImageFileFormat>(format)) ? 0 : Fail("image saving failed");
+    if (!path || format < 0 || format > 4) return Fail("pupil_image_save: bad arguments");
+    const util::DisplayTransform display{ format == 4, true }; // 3: png as the canvas shows it by default, 4: with ACES tone mapping
+    return util::SaveImage(rgba, width, height, path, static_cast<util::EImageFileFormat>(format > 3 ? 3 : format), display) ? 0 : Fail("image saving failed");
 }
 int pupil_save_buffer(const char *name, const char *path, int format) {
-    if (!Ready() || !name || !path || format < 0 || format > 2) return Fail("pupil_save_buffer: bad arguments / no scene");
+    if (!Ready() || !name || !path || format < 0 || format > 4) return Fail("pupil_save_buffer: bad arguments / no scene");
     Buffer *b = util::Singleton<BufferManager>::instance()->GetBuffer(name);
     if (!b || !b->cuda_ptr || b->desc.stride_in_byte != 16) return Fail("pupil_save_buffer: no such float4 buffer");
     std::vector<float> host(static_cast<size_t>(b->desc.width) * b->desc.height * 4);
     if (pb2_download(host.data(), b->cuda_ptr, host.size() * sizeof(float)) != PB2_OK) return Fail(pb2_last_error());
-    return util::SaveImage(host.data(), b->desc.width, b->desc.height, path, static_cast<util::EImageFileFormat>(format)) ? 0 : Fail("image saving failed");
+    const util::DisplayTransform display{ format == 4, true };
+    return util::SaveImage(host.data(), b->desc.width, b->desc.height, path, static_cast<util::EImageFileFormat>(format > 3 ? 3 : format), display) ? 0
+                                                                                                                                                   : Fail("image saving failed");
 }
 int pupil_get_env_tables(uint32_t *map_w, uint32_t *map_h, float *row_cdf, float *row_weight, float *col_cdf) {
     if (!HasWorld()) return Fail("no scene");
@@ -115,6 +118,15 @@ int pupil_get_env_tables(uint32_t *map_w, uint32_t *map_h, float *row_cdf, float
         if (dst && !src.empty()) std::memcpy(dst, src.data(), src.size() * sizeof(float));
     };
     copy(row_cdf, W()->emitters->GetEnvRowCdf()), copy(row_weight, W()->emitters->GetEnvRowWeight()), copy(col_cdf, W()->emitters->GetEnvColCdf());
+    return 0;
+}
+int pupil_set_instance_transform(uint32_t index, const float xform[16]) {
+    if (!HasWorld() || !xform) return Fail("no scene");
+    world::RenderObject *ro = W()->GetRenderObject(static_cast<size_t>(index));
+    if (!ro) return Fail("no such render object");
+    util::Transform t;
+    std::memcpy(t.matrix.e, xform, sizeof(float) * 16);
+    ro->UpdateTransform(t); // EWorldEvent::RenderInstanceTransform -> emitters reset, acceleration structure dirty, pass restarts
     return 0;
 }
 int pupil_clear_shapes(void) {

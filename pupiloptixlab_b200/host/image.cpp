@@ -534,7 +534,56 @@ bool SaveExr(const float *data, size_t w, size_t h, const std::string &path) {
     const bool ok = std::fwrite(o.data(), 1, o.size(), f) == o.size();
     return std::fclose(f) == 0 && ok;
 }
+// 8-bit RGB PNG of the displayed picture: filter type 0 on every row, one zlib stream
+bool SavePng(const float *data, size_t w, size_t h, const std::string &path, DisplayTransform display) {
+    std::vector<uint8_t> raw(h * (1 + w * 3));
+    for (size_t y = 0; y < h; ++y) {
+        uint8_t *row = &raw[y * (1 + w * 3)];
+        *row++ = 0;
+        const float *src = data + (h - 1 - y) * w * 4; // flip: buffer row 0 is the bottom of the picture
+        for (size_t x = 0; x < w; ++x) {
+            float c[3];
+            DisplayColor(src + x * 4, display, c);
+            for (int k = 0; k < 3; ++k) { // UNORM render target: clamp, scale, round to nearest
+                const float v = c[k] < 0.f || c[k] != c[k] ? 0.f : (c[k] > 1.f ? 1.f : c[k]);
+                *row++ = static_cast<uint8_t>(v * 255.f + 0.5f);
+            }
+        }
+    }
+    uLongf clen = compressBound(static_cast<uLong>(raw.size()));
+    std::vector<uint8_t> comp(clen);
+    if (compress(comp.data(), &clen, raw.data(), static_cast<uLong>(raw.size())) != Z_OK) return false;
+    std::vector<uint8_t> o = { 0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a };
+    auto be32 = [&](uint32_t v) { o.push_back(v >> 24), o.push_back(v >> 16 & 255), o.push_back(v >> 8 & 255), o.push_back(v & 255); };
+    auto chunk = [&](const char *type, const uint8_t *body, size_t n) {
+        be32(static_cast<uint32_t>(n));
+        const size_t at = o.size();
+        o.insert(o.end(), type, type + 4);
+        o.insert(o.end(), body, body + n);
+        be32(static_cast<uint32_t>(crc32(0L, o.data() + at, static_cast<uInt>(n + 4))));
+    };
+    uint8_t ihdr[13] = { uint8_t(w >> 24), uint8_t(w >> 16), uint8_t(w >> 8), uint8_t(w), uint8_t(h >> 24), uint8_t(h >> 16), uint8_t(h >> 8), uint8_t(h), 8, 2, 0, 0, 0 };
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", comp.data(), clen);
+    chunk("IEND", nullptr, 0);
+    std::FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const bool ok = std::fwrite(o.data(), 1, o.size(), f) == o.size();
+    return std::fclose(f) == 0 && ok;
+}
 }// namespace
+
+void DisplayColor(const float rgb_in[3], DisplayTransform display, float rgb_out[3]) noexcept {
+    for (int k = 0; k < 3; ++k) {
+        float c = rgb_in[k];
+        if (display.tone_mapping) { // ACESToneMapping(color, adapted_lum = 1), output.hlsl:30-40
+            const float A = 2.51f, B = 0.03f, Cc = 2.43f, D = 0.59f, E = 0.14f;
+            c = (c * (A * c + B)) / (c * (Cc * c + D) + E);
+        }
+        if (display.gamma_correct) c = std::pow(c, 1.f / 2.2f); // GammaCorrection(color, 2.2), :42-48
+        rgb_out[k] = c;
+    }
+}
 
 bool LoadImage(std::string_view path, Image &out) noexcept {
     try {
@@ -563,7 +612,7 @@ bool LoadImage(std::string_view path, Image &out) noexcept {
     }
 }
 
-bool SaveImage(const float *data, size_t w, size_t h, std::string_view path, EImageFileFormat format) noexcept {
+bool SaveImage(const float *data, size_t w, size_t h, std::string_view path, EImageFileFormat format, DisplayTransform display) noexcept {
     try {
         if (!data || !w || !h) return false;
         const std::string p(path);
@@ -572,6 +621,7 @@ bool SaveImage(const float *data, size_t w, size_t h, std::string_view path, EIm
             case EImageFileFormat::HDR: ok = SaveHdr(data, w, h, p); break;
             case EImageFileFormat::EXR: ok = SaveExr(data, w, h, p); break;
             case EImageFileFormat::PFM: ok = SavePfm(data, w, h, p); break;
+            case EImageFileFormat::PNG: ok = SavePng(data, w, h, p, display); break;
         }
         if (ok) Log::Info("image was saved successfully in [%s].", p.c_str());
         else Log::Warn("image saving failed.");

@@ -23,7 +23,13 @@ struct Image {
 // BitmapTexture::Load: false (and a warning) when the file is missing, malformed or of an unsupported kind
 bool LoadImage(std::string_view path, Image &out) noexcept;
 
-enum class EImageFileFormat { HDR, EXR, PFM };
-// BitmapTexture::Save: `data` is w*h RGBA float, row 0 = bottom of the picture
-bool SaveImage(const float *data, size_t w, size_t h, std::string_view path, EImageFileFormat format) noexcept;
+enum class EImageFileFormat { HDR, EXR, PFM, PNG };
+// BitmapTexture::Save: `data` is w*h RGBA float, row 0 = bottom of the picture.  PNG stores what the reference's canvas shows
+// (framework/system/gui/output.hlsl:30-72, gui.cpp:60-61): optional ACES tone mapping, gamma 2.2 (defaults: off, on), 8 bit.
+struct DisplayTransform {
+    bool tone_mapping = false, gamma_correct = true;
+};
+bool SaveImage(const float *data, size_t w, size_t h, std::string_view path, EImageFileFormat format, DisplayTransform display = {}) noexcept;
+// output.hlsl PSMain for one pixel: rgb in, display-referred rgb in [0, 1] out (not clamped by the shader; the render target is)
+void DisplayColor(const float rgb_in[3], DisplayTransform display, float rgb_out[3]) noexcept;
 }// namespace Pupil::util

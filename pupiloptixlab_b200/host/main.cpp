@@ -1,7 +1,7 @@
 // path_tracer — headless counterpart of example/path_tracer/main.cpp:5-22:
 //   System::Init -> AddPass(PTPass) -> SetScene(xml) -> Run -> Destroy
 // plus what a window-less run needs: an spp limit and an image file.
-//   path_tracer --scene file.xml [--spp 64] [--depth N] [--device 0] [--out image.pfm|.exr|.hdr] [--batch 16] [--builder 0|1]
+//   path_tracer --scene file.xml [--spp 64] [--depth N] [--device 0] [--out image.pfm|.exr|.hdr|.png] [--batch 16] [--builder 0|1]
 #include "pt_pass.h"
 
 #include <cstdlib>
@@ -18,7 +18,7 @@ using namespace Pupil;
 // follows the file extension.
 static bool WriteImage(const char *path, const std::vector<float> &rgba, uint32_t w, uint32_t h) {
     const std::string ext = std::filesystem::path(path).extension().string();
-    const util::EImageFileFormat fmt = ext == ".exr" ? util::EImageFileFormat::EXR : ext == ".hdr" ? util::EImageFileFormat::HDR : util::EImageFileFormat::PFM;
+    const util::EImageFileFormat fmt = ext == ".exr" ? util::EImageFileFormat::EXR : ext == ".hdr" ? util::EImageFileFormat::HDR : ext == ".png" ? util::EImageFileFormat::PNG : util::EImageFileFormat::PFM;
     return util::SaveImage(rgba.data(), w, h, path, fmt);
 }
 
@@ -37,7 +37,7 @@ int main(int argc, char **argv) {
         else if (!std::strcmp(argv[i], "--builder")) builder = std::atoi(next());
         else if (!std::strcmp(argv[i], "--verbose")) Log::level = 2;
         else {
-            std::fprintf(stderr, "usage: %s --scene file.xml [--spp N] [--depth N] [--device D] [--out image.pfm|.exr|.hdr] [--batch N] [--builder 0|1]\n", argv[0]);
+            std::fprintf(stderr, "usage: %s --scene file.xml [--spp N] [--depth N] [--device D] [--out image.pfm|.exr|.hdr|.png] [--batch N] [--builder 0|1]\n", argv[0]);
             return 2;
         }
     }

@@ -434,6 +434,7 @@ void World::RebuildDeviceScene() noexcept {
     if (!m_pb2) Pb2Check(pb2_scene_create(&m_pb2), "pb2_scene_create");
     if (!m_pb2) return;
     Pb2Check(pb2_scene_clear(m_pb2), "pb2_scene_clear");
+    emitters->Invalidate(); // pb2_scene_clear drops the emitter table with the geometry
     if (m_builder >= 0) Pb2Check(pb2_scene_set_builder(m_pb2, m_builder), "pb2_scene_set_builder");
     std::unordered_map<uint32_t, uint32_t> mesh_of_shape;
     int emitter_index_offset = 0;

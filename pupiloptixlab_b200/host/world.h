@@ -71,6 +71,7 @@ public:
     const std::vector<float> &GetEnvColCdf() const noexcept { return m_col_cdf; }
     // replaces GetEmitterGroup(): uploads the table when it changed
     void Upload(pb2_scene *scene) noexcept;
+    void Invalidate() noexcept { m_dirty = true; } // the device scene was cleared: upload again
 
 private:
     void SetMeshAreaEmitter(const resource::ShapeInstance &ins, size_t offset) noexcept;

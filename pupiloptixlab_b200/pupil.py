@@ -55,7 +55,7 @@ def lib():
             "pupil_camera_rotate": [f32, f32], "pupil_camera_set_fov": [f32],
             "pupil_register_image": [C.c_char_p, vp, u32, u32], "pupil_image_load": [C.c_char_p, P(u32), P(u32), vp, u64],
             "pupil_image_save": [C.c_char_p, vp, u32, u32, C.c_int], "pupil_save_buffer": [C.c_char_p, C.c_char_p, C.c_int],
-            "pupil_get_env_tables": [P(u32), P(u32), vp, vp, vp],
+            "pupil_get_env_tables": [P(u32), P(u32), vp, vp, vp], "pupil_set_instance_transform": [u32, P(f32)],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -116,7 +116,13 @@ def load_scene(desc: SceneDesc, host_only: bool = False):
     check(fn(to_xml_string(desc, names).encode(), None))
 
 
-IMAGE_FORMATS = dict(hdr=0, exr=1, pfm=2)
+IMAGE_FORMATS = dict(hdr=0, exr=1, pfm=2, png=3, png_aces=4)
+
+
+def set_instance_transform(index: int, xform):
+    """RenderObject::UpdateTransform: row-major 4x4 object-to-world matrix of the index-th render object"""
+    m = np.ascontiguousarray(xform, np.float32).reshape(16)
+    check(lib().pupil_set_instance_transform(index, m.ctypes.data_as(C.POINTER(f32))))
 
 
 def image_load(path) -> np.ndarray:

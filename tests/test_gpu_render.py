@@ -224,6 +224,29 @@ def test_converged_relmse_vs_oracle(port_lib):
     assert relmse < 1e-3, relmse
 
 
+def test_instance_edit_rebuilds_and_restarts(port_lib):
+    """(f4) moving a render object: acceleration structure rebuilt, emitters reset, accumulation restarted — same image as a
+    scene loaded with that transform"""
+    desc = scenes.cornell_box(64, 64, 6)
+    box = 6  # the short box
+    fresh = scenes.cornell_box(64, 64, 6)
+    fresh.shapes[box].to_world = scenes.Xf("srt", scale=(0.25, 0.4, 0.25), rotate_axis=(0, 1, 0), rotate_angle=35.0, translate=(0.2, 0.4, 0.1))
+    xf = orc.OracleScene(port_lib, fresh).instance_xform(box)
+    pupil.load_scene(fresh)
+    pupil.pass_config(frames_per_run=4)
+    pupil.run(1)
+    want = pupil.buffer("pt accum buffer").copy()
+    pupil.load_scene(desc)
+    pupil.pass_config(frames_per_run=4)
+    pupil.run(1)
+    before = pupil.buffer("pt accum buffer").copy()
+    pupil.set_instance_transform(box, xf)
+    pupil.run(1)
+    assert pupil.pass_state()[0] == 4  # restarted, not 8 samples
+    got = pupil.buffer("pt accum buffer")
+    assert not np.array_equal(got, before) and np.array_equal(got, want)
+
+
 def test_camera_edit_restarts_accumulation():
     desc = scenes.cornell_box(32, 32, 4)
     pupil.load_scene(desc)

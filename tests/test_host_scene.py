@@ -209,3 +209,23 @@ def test_reference_scene_files_load_unchanged(name, n_inst, n_area, has_env):
         w, h, depth = pupil.film()
         assert (w, h) == (512, 512)
         assert all(i["material"].type == pb2.MAT["diffuse"] and i["material"].twosided for i in ins)
+
+
+def test_instance_transform_update_matches_a_fresh_scene(port_lib):
+    """RenderObject::UpdateTransform -> World's RenderInstanceTransform handler (world.cpp:15-43): the object's area emitters
+    are rebuilt in place and the selection probabilities recomputed, exactly as if the scene had been loaded that way"""
+    desc = scenes.cornell_box(48, 48, 6)
+    pupil.load_scene(desc, host_only=True)
+    lamp = [i for i, sh in enumerate(desc.shapes) if sh.emitter is not None][0]
+    moved = scenes.Xf("srt", scale=(0.3, 0.2, 1.0), rotate_axis=(1, 0, 0), rotate_angle=80.0, translate=(0.1, 1.7, 0.2))
+    fresh = scenes.cornell_box(48, 48, 6)
+    fresh.shapes[lamp].to_world = moved
+    o = orc.OracleScene(port_lib, fresh)
+    pupil.set_instance_transform(lamp, o.instance_xform(lamp))
+    ins = pupil.instances()
+    assert np.array_equal(ins[lamp]["xform"], o.instance_xform(lamp))
+    areas, _ = pupil.emitters()
+    for a, b in zip(areas, o.area_emitters()):
+        assert a.weight == b.weight and a.select_probability == b.select_probability and a.area == b.area
+        for k in range(3):
+            assert list(a.pos[k]) == list(b.pos[k]) and list(a.nrm[k]) == list(b.nrm[k])

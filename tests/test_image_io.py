@@ -177,6 +177,25 @@ def test_pfm_and_hdr_and_exr_writers_round_trip(tmp_path):
     assert np.all(np.abs(got[..., :3] - buf[::-1, :, :3]) <= buf[::-1, :, :3].max(-1, keepdims=True) / 128 + 1e-6)
 
 
+def test_png_display_output(tmp_path):
+    """what the reference's canvas shows (system/gui/output.hlsl:30-72): gamma 2.2 by default, ACES tone mapping on request"""
+    rng = np.random.default_rng(6)
+    buf = np.ones((17, 23, 4), F)
+    buf[..., :3] = (rng.random((17, 23, 3)) ** 2 * 3.0).astype(F)  # some values above 1
+    pupil.image_save(tmp_path / "g.png", buf, "png")
+    got = pupil.image_load(tmp_path / "g.png")  # the reader linearises 8-bit sources again: pow(x / 255, 2.2)
+    want = np.clip(buf[::-1, :, :3], 0, 1)
+    u8 = np.floor(np.power(want, F(1 / 2.2)) * 255 + 0.5)
+    assert np.allclose(got[..., :3], np.power(u8 / 255, 2.2), atol=1e-6) and np.abs(got[..., :3] - want).max() < 0.02
+    pupil.image_save(tmp_path / "a.png", buf, "png_aces")
+    got = pupil.image_load(tmp_path / "a.png")
+    c = buf[::-1, :, :3].astype(np.float64)
+    aces = (c * (2.51 * c + 0.03)) / (c * (2.43 * c + 0.59) + 0.14)
+    u8 = np.floor(np.clip(np.power(aces, 1 / 2.2), 0, 1) * 255 + 0.5)
+    back = np.round(np.power(got[..., :3].astype(np.float64), 1 / 2.2) * 255)
+    assert np.abs(back - u8).max() <= 1  # fp32 pow on either side of a rounding boundary
+
+
 def _exr(path, img, compression, half):
     """minimal scan-line EXR written by hand: channels A? no — B, G, R (+ optional HALF), compression 0 / 2 / 3"""
     h, w = img.shape[:2]
