@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
         // the next iteration's queue entry is fetched now and its three 32-byte records are requested while this path is
         // shaded: ncu showed a third of k_shade's stall samples waiting on exactly these loads (profiles/r1c_ncu.md)
         valid_next = vi + stride < total && fetch(vi + stride, p_next);
+#if PB2_SHADE_PREFETCH < 3
         if (valid_next) {
 #if PB2_SHADE_PREFETCH == 1
             prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.ps + 2 * (size_t)p_next);
@@ -538,7 +539,18 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
 #endif
         }
 #endif
+#endif
         if (valid) emitted = shade_path(sv, pa, fp, out, p, sh);
+#if PB2_SHADE_PREFETCH >= 3
+        // variant: the queue entry has arrived by now, so the prefetches do not wait for it
+        if (valid_next) {
+#if PB2_SHADE_PREFETCH == 3
+            prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.ps + 2 * (size_t)p_next);
+#else
+            prefetch_l1(pa.hit + 2 * (size_t)p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.ps + 2 * (size_t)p_next);
+#endif
+        }
+#endif
 #if !PB2_SHADE_PREFETCH
         valid_next = vi + stride < total && fetch(vi + stride, p_next);
 #endif
