@@ -465,26 +465,27 @@ __global__ void __launch_bounds__(256) k_bin(SceneView sv, PathArrays pa, const 
 // Order-preserving append of a 128-thread CTA to two queues at once: thread order is kept inside the CTA's slice
 // (a CTA works on 128 consecutive queue entries, so runs of ascending path slots survive compaction and the next
 // kernel's record accesses stay close to sequential), one atomic per queue per CTA.
-__device__ __forceinline__ void block_append2(uint32_t *counter_a, uint32_t *counter_b, bool pred_a, bool pred_b, uint32_t &pos_a, uint32_t &pos_b) {
-    __shared__ uint32_t s_cnt[2][4], s_base[2];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void block_append2(uint32_t *counter_a, uint32_t *counter_b, bool pred_a, bool pred_b, uint32_t &pos_a, uint32_t &pos_b, uint32_t parity) {
+    // two copies of the scratch words, used alternately by successive calls (`parity`): the next call writes the other copy
+    // and the call after that is two barriers away, so no third barrier is needed to protect the reads below
+    __shared__ uint32_t s_cnt[2][2][4], s_base[2][2];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, b = parity & 1u;
     const uint32_t ma = __ballot_sync(0xffffffffu, pred_a), mb = __ballot_sync(0xffffffffu, pred_b);
-    if (lane == 0) s_cnt[0][warp] = __popc(ma), s_cnt[1][warp] = __popc(mb);
+    if (lane == 0) s_cnt[b][0][warp] = __popc(ma), s_cnt[b][1][warp] = __popc(mb);
     __syncthreads();
     if (threadIdx.x < 2) {
         uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-            const uint32_t c = s_cnt[threadIdx.x][w];
-            s_cnt[threadIdx.x][w] = run;
+            const uint32_t c = s_cnt[b][threadIdx.x][w];
+            s_cnt[b][threadIdx.x][w] = run;
             run += c;
         }
-        s_base[threadIdx.x] = run ? atomicAdd(threadIdx.x ? counter_b : counter_a, run) : 0u;
+        s_base[b][threadIdx.x] = run ? atomicAdd(threadIdx.x ? counter_b : counter_a, run) : 0u;
     }
     __syncthreads();
-    pos_a = s_base[0] + s_cnt[0][warp] + __popc(ma & lanemask_lt());
-    pos_b = s_base[1] + s_cnt[1][warp] + __popc(mb & lanemask_lt());
-    __syncthreads(); // s_cnt / s_base are reused by the next iteration
+    pos_a = s_base[b][0] + s_cnt[b][0][warp] + __popc(ma & lanemask_lt());
+    pos_b = s_base[b][1] + s_cnt[b][1][warp] + __popc(mb & lanemask_lt());
 }
 
 // MINB = resident CTAs per SM the register allocator must allow: 4 -> 114 registers, no spills; 6 -> 80 registers,
@@ -519,7 +520,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
         return true;
     };
     const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t p_next = 0;
+    uint32_t p_next = 0, iter = 0;
     bool valid_next = blockIdx.x * blockDim.x + threadIdx.x < total && fetch(blockIdx.x * blockDim.x + threadIdx.x, p_next);
     for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total; vi += stride) { // total % 128 == 0: CTA-uniform
         uint32_t emitted = 0;
@@ -555,7 +556,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
         valid_next = vi + stride < total && fetch(vi + stride, p_next);
 #endif
         uint32_t ps, pe;
-        block_append2(out.n_shadow, out.n_ext, emitted & 1u, emitted & 2u, ps, pe);
+        block_append2(out.n_shadow, out.n_ext, emitted & 1u, emitted & 2u, ps, pe, iter++);
         if (emitted & 1u) { // consecutive threads write consecutive 48-byte queue entries
             pa.shq[3 * (size_t)ps] = make_float4(sh.o.x, sh.o.y, sh.o.z, sh.tmax);
             pa.shq[3 * (size_t)ps + 1] = make_float4(sh.d.x, sh.d.y, sh.d.z, __uint_as_float(p));
