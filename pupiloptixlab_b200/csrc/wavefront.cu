@@ -35,7 +35,7 @@ enum { CTR_EXT = 0, CTR_SHADOW = 1, CTR_MAT0 = 2 /* ..9 */, CTR_WORK_EXT = 10, C
 // HBM-bound shade kernel of one batch runs next to the issue-bound trace kernels of the other (profiles/README.md).
 struct Lane {
     uint64_t capacity = 0;
-    DevBuf<float4> ray, hit, ps, shq; // 32-byte records per path slot (ray, hit, ps) and 48-byte shadow-queue entries (shq)
+    DevBuf<float4> ray, hit, thr, rad, shq; // 32-byte ray / hit records, 16-byte throughput|rng and radiance records per path slot; 48-byte shadow-queue entries
     DevBuf<uint32_t> q_ext[2], q_mat;
     DevBuf<uint32_t> counters; // (max_depth + 2) rounds x kCtrPerRound
     uint32_t rounds_alloc = 0;
@@ -45,7 +45,7 @@ struct Lane {
     void ensure(uint64_t paths, uint32_t rounds) {
         if (paths > capacity) {
             capacity = paths;
-            ray.alloc(paths * 2), hit.alloc(paths * 2), ps.alloc(paths * 2), shq.alloc(paths * 3);
+            ray.alloc(paths * 2), hit.alloc(paths * 2), thr.alloc(paths), rad.alloc(paths), shq.alloc(paths * 3);
             q_ext[0].alloc(paths), q_ext[1].alloc(paths), q_mat.alloc(paths * kNumTypes);
         }
         if (rounds > rounds_alloc) {
@@ -97,14 +97,17 @@ namespace {
 // sectors; fields are grouped by WRITER so no kernel writes a partial record it has not read:
 //   ray[2p]   = o.xyz | bits(state: depth | lobe << 16)     ray[2p+1] = d.xyz | bsdf pdf      generate / shade
 //   hit[2p]   = t, u, v | bits(prim)                        hit[2p+1] = bits(inst), -, -, -   extend
-//   ps[2p]    = throughput.xyz | bits(rng)                  ps[2p+1]  = radiance.xyz | -      generate / shade (+ shadow: radiance half)
+//   thr[p]    = throughput.xyz | bits(rng)                                                    generate / shade
+//   rad[p]    = radiance.xyz | -     touched only by the vertices that add to it: emitter hits and misses in shade, unoccluded
+//               shadow rays — most vertices add nothing, so the record is its own 16-byte array instead of the second half of a
+//               sector that every vertex would read and write (adjacent path slots share the sector, and queues stay in slot order)
 // Shadow rays are created and consumed exactly once, so their payload travels with the queue instead:
 //   shq[3k]   = o.xyz | tmax      shq[3k+1] = d.xyz | bits(p)      shq[3k+2] = contribution.xyz | -
 // (extension rays always use tmin 1e-3 / tmax 1e16 and shadow rays tmin 1e-4: main.cu:82-83, emitter.h:93-96)
 // (Packing the three records of a slot into one 128-byte line was measured and is slower: -8 % Msamples/s, the
 // streaming kernels then stride over unused sectors; see profiles/README.md.)
 struct PathArrays {
-    float4 *ray, *hit, *ps, *shq;
+    float4 *ray, *hit, *thr, *rad, *shq;
 };
 constexpr float kExtendTmin = 0.001f, kExtendTmax = 1e16f, kShadowTmin = 0.0001f;
 struct FrameParams {
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(256) k_generate(PathArrays pa, FrameParams fp,
         const float3 dir = dw * __fdiv_rn(1.0f, __fsqrt_rn(dot(dw, dw))); // :73 normalize
         pa.ray[2 * (size_t)p] = make_float4(cam.c2w[0].w, cam.c2w[1].w, cam.c2w[2].w, __uint_as_float(0u)); // :75-78; state = depth 0
         pa.ray[2 * (size_t)p + 1] = make_float4(dir.x, dir.y, dir.z, 0.f);
-        pa.ps[2 * (size_t)p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(rng));
-        pa.ps[2 * (size_t)p + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        pa.thr[p] = make_float4(1.f, 1.f, 1.f, __uint_as_float(rng));
+        pa.rad[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         q_ext[p] = p;
     }
 }
@@ -214,9 +217,9 @@ struct ShadowIO {
         if (valid && !hit) { // main.cu:127 `if (!occluded)`
             const uint32_t p = __float_as_uint(pa.shq[3 * (size_t)i + 1].w);
             const float4 c = pa.shq[3 * (size_t)i + 2];
-            float4 r = pa.ps[2 * (size_t)p + 1];
+            float4 r = pa.rad[p];
             r.x += c.x, r.y += c.y, r.z += c.z;
-            pa.ps[2 * (size_t)p + 1] = r;
+            pa.rad[p] = r;
             if (unoccluded) atomicAdd(unoccluded, 1ull);
         }
     }
@@ -301,14 +304,21 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
     const int32_t inst = __float_as_int(pa.hit[2 * (size_t)p + 1].x);
     const float4 ro4 = pa.ray[2 * (size_t)p], rd4 = pa.ray[2 * (size_t)p + 1];
     const float3 ray_o = mk3(ro4), ray_d = mk3(rd4);
-    const float4 thr4 = pa.ps[2 * (size_t)p], rad4 = pa.ps[2 * (size_t)p + 1];
+    const float4 thr4 = pa.thr[p];
     float3 throughput = mk3(thr4);
     const float bsdf_pdf = rd4.w;
     const uint32_t st = __float_as_uint(ro4.w);
     uint32_t depth = st & 0xffffu;
     const uint32_t sampled_type = st >> 16;
     uint32_t rng = __float_as_uint(thr4.w);
-    float3 radiance = mk3(rad4);
+    float3 radiance = mk3(0.f); // what this vertex adds to the path's radiance (at most one term: emission, or the environment on a miss)
+    auto add_radiance = [&]() {
+        if (radiance.x != 0.f || radiance.y != 0.f || radiance.z != 0.f) {
+            float4 r = pa.rad[p];
+            r.x += radiance.x, r.y += radiance.y, r.z += radiance.z;
+            pa.rad[p] = r;
+        }
+    };
     // p = frame * n_pixels + pixel; only the AOV frame needs the pixel, so no per-path integer division
     const uint32_t pixel = p - out.aov_first_slot;
     const bool write_aov = depth == 0 && out.aov_first_slot != ~0u && pixel < fp.n_pixels;
@@ -328,7 +338,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
             env_radiance *= throughput * mis;
         }
         radiance += env_radiance; // :188
-        pa.ps[2 * (size_t)p + 1] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
+        add_radiance();
         return 0u;
     }
 
@@ -371,10 +381,8 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
         if (rng_next(rng) > rr) alive = false;
         else throughput /= rr;
     }
-    if (!alive) {
-        pa.ps[2 * (size_t)p + 1] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
-        return 0u;
-    }
+    add_radiance();
+    if (!alive) return 0u;
     const Onb frame_onb(geo.normal);
     const float3 wo = frame_onb.to_local(-ray_d);
     uint32_t emitted = 0;
@@ -416,11 +424,10 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
             const float3 dir = frame_onb.to_world(rec.wi);
             pa.ray[2 * (size_t)p] = make_float4(geo.position.x, geo.position.y, geo.position.z, __uint_as_float(depth | (rec.type << 16)));
             pa.ray[2 * (size_t)p + 1] = make_float4(dir.x, dir.y, dir.z, rec.pdf);
-            pa.ps[2 * (size_t)p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(rng));
+            pa.thr[p] = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(rng));
             emitted |= 2u;
         }
     }
-    pa.ps[2 * (size_t)p + 1] = make_float4(radiance.x, radiance.y, radiance.z, 0.f);
     return emitted;
 }
 
@@ -534,9 +541,9 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
 #if PB2_SHADE_PREFETCH < 3
         if (valid_next) {
 #if PB2_SHADE_PREFETCH == 1
-            prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.ps + 2 * (size_t)p_next);
+            prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.thr + p_next);
 #else
-            prefetch_l1(pa.hit + 2 * (size_t)p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.ps + 2 * (size_t)p_next);
+            prefetch_l1(pa.hit + 2 * (size_t)p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.thr + p_next);
 #endif
         }
 #endif
@@ -546,9 +553,9 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
         // variant: the queue entry has arrived by now, so the prefetches do not wait for it
         if (valid_next) {
 #if PB2_SHADE_PREFETCH == 3
-            prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.ps + 2 * (size_t)p_next);
+            prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.thr + p_next);
 #else
-            prefetch_l1(pa.hit + 2 * (size_t)p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.ps + 2 * (size_t)p_next);
+            prefetch_l1(pa.hit + 2 * (size_t)p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.thr + p_next);
 #endif
         }
 #endif
@@ -584,7 +591,7 @@ __global__ void __launch_bounds__(256) k_accumulate(const float4 *__restrict__ r
         float3 acc = (mode != 0 && (sample_cnt0 > 0 || mode == 2)) ? mk3(accum[px]) : mk3(0.f);
         float w = mode == 2 ? accum[px].w : 1.f;
         for (uint32_t f = 0; f < frames; ++f) {
-            const float3 r = mk3(rad[2 * ((size_t)f * n_pixels + px) + 1]); // radiance half of the ps record
+            const float3 r = mk3(rad[(size_t)f * n_pixels + px]);
             if (mode == 2) { // plain sum for sample-sharded multi-GPU rendering
                 acc += r;
                 w += 1.f;
@@ -675,7 +682,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
     for (uint32_t f0 = 0; f0 < n_frames; f0 += S, ++batch) {
         Lane &ln = wf.lane[batch % n_lanes];
         st = ln.stream;
-        PathArrays pa{ ln.ray.ptr, ln.hit.ptr, ln.ps.ptr, ln.shq.ptr };
+        PathArrays pa{ ln.ray.ptr, ln.hit.ptr, ln.thr.ptr, ln.rad.ptr, ln.shq.ptr };
         const uint32_t frames = std::min(S, n_frames - f0);
         const uint32_t n_paths = frames * n_pixels;
         FrameParams fp{ lp.width, lp.height, n_pixels, lp.max_depth, lp.random_seed + f0 * (lp.seed_stride ? lp.seed_stride : 1u),
@@ -751,7 +758,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
         if (batch > 0 && n_lanes == 2) PB2_CUDA(cudaStreamWaitEvent(st, wf.lane[(batch - 1) % n_lanes].accumulated, 0));
         stage_begin(4);
         k_accumulate<<<(unsigned)std::min<uint64_t>((n_pixels + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>(
-            ln.ps.ptr, n_pixels, frames, lp.accumulate, sample_cnt, (float4 *)lp.accum_buffer, (float4 *)lp.frame_buffer);
+            ln.rad.ptr, n_pixels, frames, lp.accumulate, sample_cnt, (float4 *)lp.accum_buffer, (float4 *)lp.frame_buffer);
         PB2_LAUNCH_CHECK();
         stage_end();
         if (n_lanes == 2) PB2_CUDA(cudaEventRecord(ln.accumulated, st));
