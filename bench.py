@@ -292,7 +292,7 @@ def main():
         cs = pupil.render_stats()
         scene.set_option("counting", 0)
         nodes_c, prims_c = cs.nodes_visited - cs.nodes_shadow, cs.prims_tested - cs.prims_shadow
-        # DESIGN.md "Algorithmic bytes" (32-byte ray and hit records, 16-byte throughput and radiance records; 48-byte shadow-queue entries; 80 B / node, 48 B / primitive)
+        # DESIGN.md "Algorithmic bytes" (32-byte ray records, 16-byte hit, throughput and radiance records; 48-byte shadow-queue entries; 80 B / node, 48 B / primitive)
         big_mesh = desc.num_triangles() * 36 > 64e6  # vertex data does not stay in L2: count the hit triangle's attributes per vertex
         ext_rays = max(cs.closest_rays - n_px * spp, 0)  # extension rays emitted by k_shade (the rest are camera rays)
         # a BVH that fits the 126 MB L2 is read from HBM once per launch, not once per visit (the Cornell box's is 2 KB and lives in L1):
@@ -301,11 +301,11 @@ def main():
         tree_c = build.bvh_bytes * n_ext / args.steps if bvh_cached else nodes_c * 80 + prims_c * 48
         tree_s = build.bvh_bytes * n_shadow / args.steps if bvh_cached else cs.nodes_shadow * 80 + cs.prims_shadow * 48
         per_step = {
-            "extend": cs.closest_rays * (4 + 32 + 32) + tree_c,
+            "extend": cs.closest_rays * (4 + 32 + 16) + tree_c,
             "shadow": cs.shadow_rays * 32 + cs.shadow_unoccluded * (16 + 16 + 16) + tree_s,
-            # per vertex: queue entry 4 + hit 32 + ray 32 + throughput|rng 16 in; per extension ray: ray record 32 + throughput|rng 16 + queue entry 4 out;
+            # per vertex: queue entry 4 + hit 16 + ray 32 + throughput|rng 16 in; per extension ray: ray record 32 + throughput|rng 16 + queue entry 4 out;
             # per shadow ray: 48-byte queue entry out (radiance records are touched by emitter hits and misses only: not counted)
-            "shade": cs.closest_rays * (4 + 80 + (40 if cs.sorted else 0) + (108 if big_mesh else 0)) + ext_rays * 52 + cs.shadow_rays * 48,
+            "shade": cs.closest_rays * (4 + 64 + (24 if cs.sorted else 0) + (108 if big_mesh else 0)) + ext_rays * 52 + cs.shadow_rays * 48,
         }
         dom = max(("extend", "shade", "shadow"), key=lambda k: stage[k])
         peak, peak_kind = load_peaks()

@@ -35,7 +35,7 @@ enum { CTR_EXT = 0, CTR_SHADOW = 1, CTR_MAT0 = 2 /* ..9 */, CTR_WORK_EXT = 10, C
 // HBM-bound shade kernel of one batch runs next to the issue-bound trace kernels of the other (profiles/README.md).
 struct Lane {
     uint64_t capacity = 0;
-    DevBuf<float4> ray, hit, thr, rad, shq; // 32-byte ray / hit records, 16-byte throughput|rng and radiance records per path slot; 48-byte shadow-queue entries
+    DevBuf<float4> ray, hit, thr, rad, shq; // 32-byte ray record, 16-byte hit, throughput|rng and radiance records per path slot; 48-byte shadow-queue entries
     DevBuf<uint32_t> q_ext[2], q_mat;
     DevBuf<uint32_t> counters; // (max_depth + 2) rounds x kCtrPerRound
     uint32_t rounds_alloc = 0;
@@ -45,7 +45,7 @@ struct Lane {
     void ensure(uint64_t paths, uint32_t rounds) {
         if (paths > capacity) {
             capacity = paths;
-            ray.alloc(paths * 2), hit.alloc(paths * 2), thr.alloc(paths), rad.alloc(paths), shq.alloc(paths * 3);
+            ray.alloc(paths * 2), hit.alloc(paths), thr.alloc(paths), rad.alloc(paths), shq.alloc(paths * 3);
             q_ext[0].alloc(paths), q_ext[1].alloc(paths), q_mat.alloc(paths * kNumTypes);
         }
         if (rounds > rounds_alloc) {
@@ -96,7 +96,7 @@ namespace {
 // of the material-sorted shade kernel and of the dynamically scheduled trace kernels never pay for half-used
 // sectors; fields are grouped by WRITER so no kernel writes a partial record it has not read:
 //   ray[2p]   = o.xyz | bits(state: depth | lobe << 16)     ray[2p+1] = d.xyz | bsdf pdf      generate / shade
-//   hit[2p]   = t, u, v | bits(prim)                        hit[2p+1] = bits(inst), -, -, -   extend
+//   hit[p]    = u, v (triangle) or t, - (sphere) | bits(prim) | bits(inst)                   extend
 //   thr[p]    = throughput.xyz | bits(rng)                                                    generate / shade
 //   rad[p]    = radiance.xyz | -     touched only by the vertices that add to it: emitter hits and misses in shade, unoccluded
 //               shadow rays — most vertices add nothing, so the record is its own 16-byte array instead of the second half of a
@@ -189,14 +189,17 @@ struct ExtendIO {
         if (valid) {
             int32_t inst = -1;
             uint32_t prim = 0;
+            bool sphere = false;
             if (hit) {
                 const float4 *rec = reinterpret_cast<const float4 *>(sv.prims + h.prim_slot);
                 prim = __float_as_uint(__ldg(rec).w);
                 inst = (int32_t)__float_as_uint(__ldg(rec + 1).w);
+                sphere = __float_as_uint(__ldg(rec + 2).w) != 0u;
                 type = (uint32_t)__ldg(&sv.instances[inst].mat_type) & 7u;
             }
-            pa.hit[2 * (size_t)p] = make_float4(h.t, h.u, h.v, __uint_as_float(prim));
-            pa.hit[2 * (size_t)p + 1] = make_float4(__int_as_float(inst), 0.f, 0.f, 0.f);
+            // 16 bytes are all the shade stage needs: barycentrics for a triangle (its position comes from the vertices), t for a
+            // sphere (position = o + t d), and the two ids
+            pa.hit[p] = make_float4(sphere ? h.t : h.u, h.v, __uint_as_float(prim), __int_as_float(inst));
         }
         // no queue work here: rays finish in scheduling order, and appending in that order would scatter the next
         // kernel's path-state accesses.  k_bin (sorted mode) or k_shade itself (unsorted) walk the queue in order.
@@ -300,8 +303,8 @@ struct ShadowRay {
 };
 // One path at one hit (or miss).  Returns bit 0: `sh` holds a shadow ray, bit 1: an extension ray was written.
 __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathArrays &pa, const FrameParams &fp, const ShadeOut &out, uint32_t p, ShadowRay &sh) {
-    const float4 hit = pa.hit[2 * (size_t)p];
-    const int32_t inst = __float_as_int(pa.hit[2 * (size_t)p + 1].x);
+    const float4 hit = pa.hit[p]; // u, v (triangle) or t (sphere), prim, inst
+    const int32_t inst = __float_as_int(hit.w);
     const float4 ro4 = pa.ray[2 * (size_t)p], rd4 = pa.ray[2 * (size_t)p + 1];
     const float3 ray_o = mk3(ro4), ray_d = mk3(rd4);
     const float4 thr4 = pa.thr[p];
@@ -346,9 +349,9 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
     const DevInstance *in = sv.instances + inst;
     const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(&in->flags)); // flags, mat_type, emitter_offset, n_tris
     const uint32_t flags = meta.x;
-    const uint32_t prim = __float_as_uint(hit.w);
+    const uint32_t prim = __float_as_uint(hit.z);
     LocalGeometry geo;
-    hit_local_geometry(in, flags, ray_o, ray_d, hit.x, hit.y, hit.z, prim, geo);
+    hit_local_geometry(in, flags, ray_o, ray_d, hit.x, hit.x, hit.y, prim, geo);
     const int emitter_index = (int)meta.z >= 0 ? (int)meta.z + (int)prim : -1;
     const LocalBsdf bsdf = get_local_bsdf(sv.materials + inst, geo.texcoord);
 
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(256) k_bin(SceneView sv, PathArrays pa, const 
         uint32_t p = 0, type = kNumTypes;
         if (valid) {
             p = q_in[i];
-            const int32_t inst = __float_as_int(pa.hit[2 * (size_t)p + 1].x);
+            const int32_t inst = __float_as_int(pa.hit[p].w);
             type = inst < 0 ? 0u : ((uint32_t)__ldg(&sv.instances[inst].mat_type) & 7u);
         }
         const uint32_t peers = __match_any_sync(0xffffffffu, type);
@@ -541,9 +544,9 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
 #if PB2_SHADE_PREFETCH < 3
         if (valid_next) {
 #if PB2_SHADE_PREFETCH == 1
-            prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.thr + p_next);
+            prefetch_l2(pa.hit + p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.thr + p_next);
 #else
-            prefetch_l1(pa.hit + 2 * (size_t)p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.thr + p_next);
+            prefetch_l1(pa.hit + p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.thr + p_next);
 #endif
         }
 #endif
@@ -553,9 +556,9 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
         // variant: the queue entry has arrived by now, so the prefetches do not wait for it
         if (valid_next) {
 #if PB2_SHADE_PREFETCH == 3
-            prefetch_l2(pa.hit + 2 * (size_t)p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.thr + p_next);
+            prefetch_l2(pa.hit + p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.thr + p_next);
 #else
-            prefetch_l1(pa.hit + 2 * (size_t)p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.thr + p_next);
+            prefetch_l1(pa.hit + p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.thr + p_next);
 #endif
         }
 #endif
