@@ -209,14 +209,34 @@ PB2_D void ray_begin(RayState &r, float3 o, float3 d, float tmin, float tmax, bo
 PB2_D bool ray_has_nodes(const RayState &r) { return (r.G.y & 0xff000000u) != 0u || r.sp > 0; }
 
 // pops the nearest pending internal node, tests its eight children, leaves the hit children in G / T
-PB2_D void node_step(const SceneView &sv, RayState &r, uint2 *stack) {
-    if (!(r.G.y & 0xff000000u)) r.G = stack[--r.sp];
+// Traversal stack of one lane: the first kSmemStack entries live in shared memory (entry-major, so the 32 lanes of a warp hit
+// 32 different banks), the rest in local memory.  ncu on the Cornell box counted 1.6 GB of DRAM traffic per k_extend launch
+// against 0.9 GB of ray / hit records: the difference was the local-memory stack (one 8-byte push per ray allocates a sector).
+#ifndef PB2_SMEM_STACK
+#define PB2_SMEM_STACK 8
+#endif
+constexpr int kSmemStack = PB2_SMEM_STACK;
+struct TravStack {
+    uint2 *sm; // this thread's column of the shared part (stride: CTA size)
+    uint2 *lo; // local-memory part
+    PB2_D void push(int &sp, uint2 v) const {
+        if (sp < kSmemStack) sm[sp * 128] = v;
+        else lo[sp - kSmemStack] = v;
+        ++sp;
+    }
+    PB2_D uint2 pop(int &sp) const {
+        --sp;
+        return sp < kSmemStack ? sm[sp * 128] : lo[sp - kSmemStack];
+    }
+};
+PB2_D void node_step(const SceneView &sv, RayState &r, const TravStack &stack) {
+    if (!(r.G.y & 0xff000000u)) r.G = stack.pop(r.sp);
     const uint32_t bit = 31u - __clz(r.G.y);
     r.G.y &= ~(1u << bit);
     const uint32_t slot = (bit - 24u) ^ r.oct;
     const uint32_t rel = __popc(r.G.y & 0xffu & ((1u << slot) - 1u));
     const Bvh8Node *np = sv.nodes + (r.G.x + rel);
-    if (r.G.y & 0xff000000u) stack[r.sp++] = r.G;
+    if (r.G.y & 0xff000000u) stack.push(r.sp, r.G);
 
     const float4 n0 = __ldg(&np->n0);
     const uint4 n1 = __ldg(&np->n1), n2 = __ldg(&np->n2), n3 = __ldg(&np->n3), n4 = __ldg(&np->n4);
@@ -281,7 +301,9 @@ PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ 
     CoopShared &sm = s_coop[COOP ? threadIdx.x >> 5 : 0];
     const uint32_t n = io.size();
     const uint32_t lane = threadIdx.x & 31u;
-    uint2 stack[PB2_STACK_SIZE];
+    __shared__ uint2 s_stack[(kSmemStack > 0 ? kSmemStack : 1) * 128]; // 128-thread CTAs (launch bounds of the trace kernels)
+    uint2 stack_local[PB2_STACK_SIZE - kSmemStack];
+    const TravStack stack{ s_stack + threadIdx.x, stack_local };
     RayState r;
     r.T = 0u, r.G = make_uint2(0u, 0u), r.sp = 0;
     uint32_t ray = 0;
