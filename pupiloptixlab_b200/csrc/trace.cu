@@ -1,5 +1,5 @@
 // Stand-alone trace kernels behind pb2_trace_closest / pb2_trace_any (parity hooks and the traversal
-// benchmark of config C4).  The wavefront integrator (wavefront.cu) uses the same traverse<>().
+// benchmark of config C4).  The wavefront integrator (wavefront.cu) uses the same trace_persistent<>().
 #include "scene.cuh"
 #include "traverse.cuh"
 

@@ -79,93 +79,8 @@ PB2_D bool intersect_prim(const SceneView &sv, uint32_t slot, float3 o, float3 d
     }
 }
 
-// Closest hit (ANY = false) or first hit (ANY = true).  `hit.t` must come in as tmax.
-template<bool ANY, bool COUNT>
-PB2_D bool traverse(const SceneView &sv, float3 o, float3 d, float tmin, RayHit &hit, TraceCounters *ctr) {
-    hit.prim_slot = 0xffffffffu;
-    if (sv.n_nodes == 0) return false;
-    auto safe_inv = [](float x) { return __frcp_rn(fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
-    const float3 idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
-    // octant: bit set <=> direction component >= 0.  Children were placed so that slot ^ oct is
-    // larger for nearer children; the highest set bit of the hit mask is visited first.
-    const bool px = idir.x >= 0.f, py = idir.y >= 0.f, pz = idir.z >= 0.f; // from idir so that -0.0 stays consistent
-    const uint32_t oct = (px ? 4u : 0u) | (py ? 2u : 0u) | (pz ? 1u : 0u);
-    const uint32_t oct4 = oct * 0x01010101u;
-
-    uint2 stack[PB2_STACK_SIZE];
-    int sp = 0;
-    uint2 G = make_uint2(0u, 0x80000000u); // (child base, hit bits 31..24 | imask 7..0): the root as a group of one
-
-    for (;;) {
-        // ---- pop the nearest pending internal child of G ----
-        const uint32_t bit = 31u - __clz(G.y);
-        G.y &= ~(1u << bit);
-        const uint32_t slot = (bit - 24u) ^ oct;
-        const uint32_t rel = __popc(G.y & 0xffu & ((1u << slot) - 1u));
-        const uint32_t node_idx = G.x + rel;
-        if (G.y & 0xff000000u) stack[sp++] = G;
-
-        const Bvh8Node *np = sv.nodes + node_idx;
-        const float4 n0 = __ldg(&np->n0);
-        const uint4 n1 = __ldg(&np->n1), n2 = __ldg(&np->n2), n3 = __ldg(&np->n3), n4 = __ldg(&np->n4);
-        if (COUNT) ++ctr->nodes;
-
-        const uint32_t ebits = __float_as_uint(n0.w);
-        const float sx = __uint_as_float((ebits & 0xffu) << 23), sy = __uint_as_float(((ebits >> 8) & 0xffu) << 23),
-                    sz = __uint_as_float(((ebits >> 16) & 0xffu) << 23);
-        const float3 adj = mk3(sx * idir.x, sy * idir.y, sz * idir.z);
-        const float3 org = mk3((n0.x - o.x) * idir.x, (n0.y - o.y) * idir.y, (n0.z - o.z) * idir.z);
-        // far planes are pushed out by a few ulps so rounding can never cull a box the ray touches
-        constexpr float kFar = 1.0000004f;
-        const float3 adj_f = adj * kFar, org_f = org * kFar;
-
-        uint32_t hitmask = 0;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const uint32_t meta4 = half ? n1.w : n1.z;
-            const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-            const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
-            const uint32_t bit_index4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1f1f1f1fu;
-            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-            const uint32_t qlx = half ? n2.y : n2.x, qly = half ? n2.w : n2.z, qlz = half ? n3.y : n3.x;
-            const uint32_t qhx = half ? n3.w : n3.z, qhy = half ? n4.y : n4.x, qhz = half ? n4.w : n4.z;
-            // near / far plane bytes per axis depend only on the ray's sign
-            const uint32_t nx = px ? qlx : qhx, fx = px ? qhx : qlx;
-            const uint32_t ny = py ? qly : qhy, fy = py ? qhy : qly;
-            const uint32_t nz = pz ? qlz : qhz, fz = pz ? qhz : qlz;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float tnx = (float)byte_of(nx, j) * adj.x + org.x, tfx = (float)byte_of(fx, j) * adj_f.x + org_f.x;
-                const float tny = (float)byte_of(ny, j) * adj.y + org.y, tfy = (float)byte_of(fy, j) * adj_f.y + org_f.y;
-                const float tnz = (float)byte_of(nz, j) * adj.z + org.z, tfz = (float)byte_of(fz, j) * adj_f.z + org_f.z;
-                const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-                const float tf = fminf(fminf(tfx, tfy), fminf(tfz, hit.t));
-                if (tn <= tf) hitmask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
-            }
-        }
-        G = make_uint2(n1.x, (hitmask & 0xff000000u) | (ebits >> 24));
-        uint32_t T = hitmask & 0x00ffffffu;
-
-        // ---- primitives of the hit leaf slots ----
-        while (T) {
-            const uint32_t i = __ffs(T) - 1;
-            T &= T - 1;
-            if (COUNT) ++ctr->prims;
-            if (intersect_prim(sv, n1.y + i, o, d, tmin, hit)) {
-                if (ANY) return true;
-            }
-        }
-        // ---- next group ----
-        if (!(G.y & 0xff000000u)) {
-            if (sp == 0) break;
-            G = stack[--sp];
-        }
-    }
-    return hit.prim_slot != 0xffffffffu;
-}
-
 // ---- persistent, dynamically refilled traversal ------------------------------------------------------------
-// The per-ray loop above leaves a warp waiting for its slowest ray (ncu, 30 M triangles, incoherent rays:
+// A plain one-ray-per-thread loop leaves a warp waiting for its slowest ray (ncu, 30 M triangles, incoherent rays:
 // 5.8 of 32 threads active per instruction).  Here every lane owns a traversal state that survives across
 // rays and the warp advances in explicit lock step: per iteration every busy lane pops and tests ONE wide node
 // and then the primitives of the leaf slots it hit; finished lanes commit their result, and as soon as fewer
