@@ -134,3 +134,32 @@ def test_axis_aligned_and_degenerate_rays(port_lib):
     ref, _ = osc.trace_closest(rays, brute=True)
     gpu = s.trace_closest(rays)
     compare_hits(gpu, ref, rays)
+
+
+def test_error_behaviour_through_the_c_abi():
+    """status codes + pb2_last_error instead of the reference's assert(false) (cuda/util.h:15-38): wrong call order and bad
+    arguments fail loudly, and the scene stays usable afterwards"""
+    from pupiloptixlab_b200.pb2 import LaunchParams, Pb2Error
+    s = pb2.Scene()
+    rays = random_rays(16, 1)
+    mesh = random_soup(10, 1)
+    mid = s.add_mesh(mesh["positions"], mesh["indices"])
+    s.add_instance(mid)
+    with pytest.raises(Pb2Error, match="pb2_bvh_build first"):
+        s.trace_closest(rays)
+    with pytest.raises(Pb2Error, match="pb2_bvh_build first"):
+        s.render(LaunchParams(max_depth=4, width=4, height=4, n_frames=1))
+    s.build()
+    with pytest.raises(Pb2Error, match="accum_buffer"):
+        s.render(LaunchParams(max_depth=4, width=4, height=4, n_frames=1))
+    with pytest.raises(Pb2Error):
+        s.add_instance(mid + 7)  # no such mesh
+    with pytest.raises(Pb2Error):
+        s.set_option("no_such_option", 1)
+    with pytest.raises(Pb2Error):
+        pb2.Bitmap(np.zeros((0, 4, 4), np.float32))
+    with pytest.raises(Pb2Error):
+        pb2.Bitmap(np.zeros((2, 2, 4), np.float32), address_mode=9)
+    assert s.trace_closest(rays[:0]).shape == (0,)  # empty batch: fine
+    hits = s.trace_closest(rays)                     # and the scene still works
+    assert hits.shape == (16,)
