@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--refill", type=str, default="", help="comma list of refill thresholds to sweep")
+    ap.add_argument("--orders", action="store_true", help="also trace the incoherent batch in three coherent orders")
     ap.add_argument("--coop", type=int, default=-1, help="warp-cooperative primitive tests: 1 on, 0 off, -1 auto")
     args = ap.parse_args()
     import torch
@@ -137,6 +138,20 @@ def main():
     inco = np.zeros((k, 8), np.float32)
     inco[:, 0:3], inco[:, 3], inco[:, 4:7], inco[:, 7] = p, 1e-3, d, 1e16
     inco = inco[rng.permutation(k)]
+    if args.orders:  # how much of the incoherent batch's cost is ordering: same rays, binned by direction octant / sorted along a Morton curve of the origins
+        octant = (inco[:, 4] >= 0) * 4 + (inco[:, 5] >= 0) * 2 + (inco[:, 6] >= 0)
+        trace(inco[np.argsort(octant, kind="stable")], False, "closest_incoherent_bounce binned by octant")
+        lo, hi = inco[:, 0:3].min(0), inco[:, 0:3].max(0)
+        q = np.clip((inco[:, 0:3] - lo) / np.maximum(hi - lo, 1e-9) * 1023, 0, 1023).astype(np.uint64)
+
+        def spread(v):
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            return (v | (v << 2)) & 0x09249249
+        morton = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+        trace(inco[np.argsort(morton, kind="stable")], False, "closest_incoherent_bounce sorted by origin (Morton)")
+        trace(inco[np.lexsort((morton, octant))], False, "closest_incoherent_bounce sorted by octant, then origin")
     for thr in sweep:
         if thr is not None:
             apply(thr)
