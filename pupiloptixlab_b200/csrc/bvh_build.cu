@@ -562,5 +562,6 @@ void build_bvh(Scene &s) {
     s.build_stats.max_depth = host_counters[3];
     if (host_counters[3] > PB2_STACK_SIZE - 2) throw std::runtime_error("pb2_bvh_build: wide tree deeper than the traversal stack (" + std::to_string(host_counters[3]) + " levels)");
     s.bvh_valid = true;
+    if (s.l2_persist_mb > 0) s.l2_dirty = true; // the node array moved
 }
 }// namespace pb2

@@ -80,6 +80,27 @@ Scene::~Scene() {
     if (wf) wavefront_destroy(wf);
     if (own_stream) cudaStreamDestroy(own_stream);
 }
+void Scene::apply_l2_window() {
+    l2_dirty = false;
+    cudaStreamAttrValue v{};
+    int dev = 0, max_persist = 0, max_window = 0;
+    PB2_CUDA(cudaGetDevice(&dev));
+    PB2_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    PB2_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
+    const size_t persist = std::min((size_t)l2_persist_mb << 20, (size_t)std::max(0, max_persist));
+    if (persist > 0 && bvh_valid && n_nodes > 0) {
+        const size_t want = l2_window_mb > l2_persist_mb ? (size_t)l2_window_mb << 20 : persist;
+        const size_t bytes = std::min(std::min((size_t)n_nodes * sizeof(Bvh8Node), (size_t)max_window), want);
+        PB2_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+        v.accessPolicyWindow.base_ptr = d_nodes.ptr;
+        v.accessPolicyWindow.num_bytes = bytes;
+        v.accessPolicyWindow.hitRatio = bytes > persist ? (float)persist / (float)bytes : 1.f;
+        v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } // else: a zero-byte window switches the policy off
+    PB2_CUDA(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
+    if (v.accessPolicyWindow.num_bytes == 0) cudaCtxResetPersistingL2Cache();
+}
 void Scene::upload_tables() {
     if (!tables_dirty) return;
     uint32_t seen = 0;
@@ -359,6 +380,7 @@ int pb2_scene_set_stream(pb2_scene *scene, void *cuda_stream) {
     Scene &s = *S(scene);
     PB2_CUDA(cudaStreamSynchronize(s.stream));
     s.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s.own_stream;
+    if (s.l2_persist_mb > 0) s.l2_dirty = true;
     return PB2_OK;
     PB2_CATCH
 }
@@ -547,6 +569,8 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     else if (n == "two_lanes") s.two_lanes = value != 0;
     else if (n == "coop_prims") s.coop_prims = (int)std::min<int64_t>(1, std::max<int64_t>(-1, value));
     else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);
+    else if (n == "l2_persist_mb") s.l2_persist_mb = (int)std::min<int64_t>(1024, std::max<int64_t>(0, value)), s.l2_dirty = true;
+    else if (n == "l2_window_mb") s.l2_window_mb = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value)), s.l2_dirty = true;
     else return fail(PB2_ERR_ARG, "pb2_scene_set_option: unknown option " + n);
     return PB2_OK;
 }

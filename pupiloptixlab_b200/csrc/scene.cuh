@@ -56,6 +56,14 @@ struct Scene {
     // auto: few lanes reach a leaf per step in deep trees (cooperation pays); in tiny scenes every lane does (it only costs)
     bool use_coop_prims() const { return coop_prims == 1 || (coop_prims < 0 && n_prims >= 4096u); } // persistent traversal: refill idle lanes when fewer than this many are busy
 
+    // "L2-resident top levels": an access-policy window over the first bytes of the node array (the collapse writes the wide
+    // tree level by level, so these are the top levels) marks them persisting in L2 for every kernel on the scene's stream.
+    // 0 = off (default; measured in profiles/README.md).  l2_window_mb > l2_persist_mb spreads the carve-out over a larger
+    // window with hit ratio persist / window.
+    int l2_persist_mb = 0, l2_window_mb = 0;
+    bool l2_dirty = false;
+    void apply_l2_window(); // pb2_api.cu; called by the launch sites when l2_dirty
+
     Wavefront *wf = nullptr;
     pb2_render_stats render_stats{};
 

@@ -79,6 +79,7 @@ template<class K, class IO>
 void launch_trace(Scene &s, K kernel_plain, K kernel_count, const IO &io, uint64_t n) {
     if (n >= 0xffffffffull) throw std::runtime_error("pb2_trace: more than 2^32-1 rays in one call");
     const SceneView sv = s.view();
+    if (s.l2_dirty) s.apply_l2_window();
     s.trace_work.ensure(1);
     PB2_CUDA(cudaMemsetAsync(s.trace_work.ptr, 0, sizeof(uint32_t), s.stream));
     if (s.counting) {

@@ -194,7 +194,13 @@ PB2_D void node_step(const SceneView &sv, RayState &r, const TravStack &stack) {
 
 // resident 128-thread CTAs per SM the trace kernels are compiled for: 9 (56 registers) with the per-lane primitive loop,
 // 8 (64 registers) with the warp-cooperative one
-#define PB2_TRACE_MINB(COOP) ((COOP) ? 8 : 9)
+#ifndef PB2_TRACE_MINB_PLAIN
+#define PB2_TRACE_MINB_PLAIN 9
+#endif
+#ifndef PB2_TRACE_MINB_COOP
+#define PB2_TRACE_MINB_COOP 8
+#endif
+#define PB2_TRACE_MINB(COOP) ((COOP) ? PB2_TRACE_MINB_COOP : PB2_TRACE_MINB_PLAIN)
 constexpr int kPairsPerLane = 8;   // primitives one lane contributes per cooperative round
 constexpr int kTraceWarps = 4;     // the trace kernels run 128-thread CTAs
 struct CoopShared {                // per warp

@@ -646,6 +646,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
     const uint32_t S = (uint32_t)std::min<uint64_t>((n_frames + n_lanes - 1) / n_lanes, std::max<uint64_t>(1, target / n_lanes / n_pixels));
     const uint32_t rounds = std::max(1u, lp.max_depth);
     if ((uint64_t)S * n_pixels >= 0xffffffffull) throw std::runtime_error("pb2_render: too many paths in flight");
+    if (s.l2_dirty) s.apply_l2_window();
     wf.lane[0].stream = s.stream, wf.lane[1].stream = wf.lane[1].own;
     for (uint32_t l = 0; l < n_lanes; ++l) wf.lane[l].ensure((uint64_t)S * n_pixels, rounds + 1);
 

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--refill", type=str, default="", help="comma list of refill thresholds to sweep")
     ap.add_argument("--orders", action="store_true", help="also trace the incoherent batch in three coherent orders")
+    ap.add_argument("--l2", type=str, default="", help="comma list of persist_mb:window_mb pairs for the L2 access-policy window over the top of the node array")
     ap.add_argument("--coop", type=int, default=-1, help="warp-cooperative primitive tests: 1 on, 0 off, -1 auto")
     args = ap.parse_args()
     import torch
@@ -166,6 +167,13 @@ def main():
         if thr is not None:
             apply(thr)
         trace(sh, True, f"anyhit_shadow_to_light thr={thr}")
+    for pair in [x for x in args.l2.split(",") if x]:
+        persist, window = (int(y) for y in pair.split(":"))
+        scene.set_option("l2_persist_mb", persist)
+        scene.set_option("l2_window_mb", window)
+        trace(prim, False, f"closest_primary_1080p l2={pair}")
+        trace(inco, False, f"closest_incoherent_bounce l2={pair}")
+        trace(sh, True, f"anyhit_shadow_to_light l2={pair}")
     pupil.shutdown()
 
 
