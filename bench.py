@@ -70,6 +70,27 @@ class ClockSampler:
         self.device, self.proc, self.path = device, None, None
 
     def start(self):
+        """NVML in a thread (a sample every 20 ms, no process start-up inside the timed region); the nvidia-smi loop is the fallback."""
+        self.samples, self.thread, self.halt = [], None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            reasons_of = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.halt.is_set():
+                    try:
+                        self.samples.append((float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), mx, int(reasons_of(h))))
+                    except Exception:
+                        pass
+                    self.halt.wait(0.02)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.path = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False).name
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
@@ -79,6 +100,17 @@ class ClockSampler:
 
     def stop(self) -> dict:
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if getattr(self, "thread", None) is not None:
+            self.halt.set()
+            self.thread.join(timeout=2)
+            if self.samples:
+                bits = 0
+                for _, _, r in self.samples:
+                    bits |= r
+                names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}  # NVML clocks-event-reason bits
+                out = {"sm_mhz": float(np.median([c for c, _, _ in self.samples])), "sm_max_mhz": self.samples[0][1],
+                       "reasons": sorted(n for b, n in names.items() if bits & b), "samples": len(self.samples), "source": "nvml"}
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()

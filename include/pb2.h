@@ -209,7 +209,10 @@ int pb2_synchronize(pb2_scene *scene);
 int pb2_render_stats_get(pb2_scene *scene, pb2_render_stats *stats); /* synchronises */
 /* options: profiling (per-stage events, serialises stages), counting (traversal counters),
  * paths_in_flight (0 = default), sort_by_material (1 on, 0 off, -1 = auto: on when the scene has more than one
- * material type; default -1), refill_threshold (persistent traversal), shade_variant (4 | 6 resident CTAs per SM) */
+ * material type; default -1), refill_threshold (persistent traversal), shade_variant (4 | 6 | 7 | 8 resident CTAs per SM),
+ * two_lanes (two batches in flight on two streams), coop_prims (warp-cooperative primitive tests: 1 on, 0 off, -1 = auto
+ * by scene size), l2_persist_mb / l2_window_mb (persisting-L2 access-policy window over the top levels of the node array;
+ * 0 = off, the default).  Unknown names fail with PB2_ERR_ARG. */
 int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value);
 /* multi-GPU shards render with accumulate = 2 (sum); after the cross-GPU reduction the root calls this:
  * frame[i] = (sum[i].xyz / total_spp, 1).   */
