@@ -1,9 +1,11 @@
 #include "image.h"
+#include "image_ldr.h"
 #include "util.h"
 
 #include <zlib.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -65,6 +67,21 @@ struct Reader {
     }
 };
 float LdrToLinear(uint8_t v) { return std::pow(v * 1.f / 255.f, 2.2f); } // texture.cpp:108-110
+// 8-bit pixels -> RGBA float the way StbImageLoad does (texture.cpp:106-117): colour through pow(x / 255, 2.2), alpha / 255,
+// alpha 1 without an alpha channel; grey is spread over R, G, B
+void FromPixels8(const ldr::Pixels8 &px, Image &img) {
+    float lut[256];
+    for (int i = 0; i < 256; ++i) lut[i] = LdrToLinear(static_cast<uint8_t>(i));
+    img.w = static_cast<size_t>(px.w), img.h = static_cast<size_t>(px.h);
+    img.rgba.resize(img.w * img.h * 4);
+    const int c = px.channels;
+    for (size_t i = 0, n = img.w * img.h; i < n; ++i) {
+        const uint8_t *s = px.data.data() + i * c;
+        float *o = &img.rgba[i * 4];
+        if (c >= 3) o[0] = lut[s[0]], o[1] = lut[s[1]], o[2] = lut[s[2]], o[3] = c == 4 ? s[3] * 1.f / 255.f : 1.f;
+        else o[0] = o[1] = o[2] = lut[s[0]], o[3] = c == 2 ? s[1] * 1.f / 255.f : 1.f;
+    }
+}
 
 // ---- PFM ("PF" colour / "Pf" grey, bottom-to-top rows, negative scale = little endian) ---------------------------
 bool LoadPfm(const std::vector<uint8_t> &file, Image &img) {
@@ -233,7 +250,7 @@ bool LoadPng(const std::vector<uint8_t> &file, Image &img) {
             break;
         }
     }
-    if (!w || !h || interlace) return false; // Adam7 is not read
+    if (!w || !h || interlace > 1) return false;
     int channels;
     switch (color) {
         case 0: channels = 1; break;
@@ -245,53 +262,75 @@ bool LoadPng(const std::vector<uint8_t> &file, Image &img) {
     }
     if (!(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) return false;
     if (color == 3 && (depth == 16 || palette.empty())) return false;
-    const size_t bpp_bits = static_cast<size_t>(channels) * depth, stride = (w * bpp_bits + 7) / 8, bpp = std::max<size_t>(1, bpp_bits / 8);
-    std::vector<uint8_t> raw(h * (stride + 1));
+    const size_t bpp_bits = static_cast<size_t>(channels) * depth, bpp = std::max<size_t>(1, bpp_bits / 8);
+    auto stride_of = [&](uint32_t pw) { return (pw * bpp_bits + 7) / 8; };
+    // the seven Adam7 passes (or the one pass of a non-interlaced file): origin and step of the sub-image inside the picture
+    struct Pass {
+        uint32_t x0, y0, dx, dy;
+    };
+    static const Pass adam7[7] = { { 0, 0, 8, 8 }, { 4, 0, 8, 8 }, { 0, 4, 4, 8 }, { 2, 0, 4, 4 }, { 0, 2, 2, 4 }, { 1, 0, 2, 2 }, { 0, 1, 1, 2 } };
+    static const Pass whole = { 0, 0, 1, 1 };
+    const Pass *passes = interlace ? adam7 : &whole;
+    const int n_passes = interlace ? 7 : 1;
+    auto pass_w = [&](const Pass &ps) { return ps.x0 < w ? (w - ps.x0 + ps.dx - 1) / ps.dx : 0u; };
+    auto pass_h = [&](const Pass &ps) { return ps.y0 < h ? (h - ps.y0 + ps.dy - 1) / ps.dy : 0u; };
+    size_t raw_size = 0;
+    for (int i = 0; i < n_passes; ++i)
+        if (pass_w(passes[i]) && pass_h(passes[i])) raw_size += pass_h(passes[i]) * (stride_of(pass_w(passes[i])) + 1);
+    std::vector<uint8_t> raw(raw_size);
     uLongf raw_len = static_cast<uLongf>(raw.size());
     if (uncompress(raw.data(), &raw_len, idat.data(), static_cast<uLong>(idat.size())) != Z_OK || raw_len != raw.size()) return false;
-    std::vector<uint8_t> prev(stride, 0), cur(stride);
     img.w = w, img.h = h;
     img.rgba.resize(static_cast<size_t>(w) * h * 4);
-    for (uint32_t y = 0; y < h; ++y) {
-        const uint8_t *line = raw.data() + y * (stride + 1);
-        const int filter = line[0];
-        for (size_t i = 0; i < stride; ++i) {
-            const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
-            int v = line[1 + i];
-            switch (filter) {
-                case 0: break;
-                case 1: v += a; break;
-                case 2: v += b; break;
-                case 3: v += (a + b) >> 1; break;
-                case 4: v += Paeth(a, b, c); break;
-                default: return false;
+    const uint8_t *src = raw.data();
+    for (int pi = 0; pi < n_passes; ++pi) {
+        const Pass &ps = passes[pi];
+        const uint32_t pw = pass_w(ps), ph = pass_h(ps);
+        if (!pw || !ph) continue; // an empty pass has no bytes at all, not even filter bytes
+        const size_t stride = stride_of(pw);
+        std::vector<uint8_t> prev(stride, 0), cur(stride);
+        for (uint32_t y = 0; y < ph; ++y) {
+            const uint8_t *line = src + y * (stride + 1);
+            const int filter = line[0];
+            for (size_t i = 0; i < stride; ++i) {
+                const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+                int v = line[1 + i];
+                switch (filter) {
+                    case 0: break;
+                    case 1: v += a; break;
+                    case 2: v += b; break;
+                    case 3: v += (a + b) >> 1; break;
+                    case 4: v += Paeth(a, b, c); break;
+                    default: return false;
+                }
+                cur[i] = static_cast<uint8_t>(v);
             }
-            cur[i] = static_cast<uint8_t>(v);
-        }
-        auto sample8 = [&](uint32_t x, int ch) -> uint8_t { // sample reduced to 8 bits the way stb_image's 8-bit API does
-            if (depth == 8) return cur[static_cast<size_t>(x) * channels + ch];
-            if (depth == 16) return cur[(static_cast<size_t>(x) * channels + ch) * 2]; // high byte
-            const size_t bit = static_cast<size_t>(x) * depth;
-            const uint8_t v = (cur[bit / 8] >> (8 - depth - bit % 8)) & ((1u << depth) - 1u);
-            return color == 3 ? v : static_cast<uint8_t>(v * (255 / ((1 << depth) - 1)));
-        };
-        for (uint32_t x = 0; x < w; ++x) {
-            uint8_t px[4] = { 0, 0, 0, 255 };
-            if (color == 3) {
-                const uint8_t idx = sample8(x, 0);
-                if (static_cast<size_t>(idx) * 3 + 2 < palette.size()) px[0] = palette[idx * 3], px[1] = palette[idx * 3 + 1], px[2] = palette[idx * 3 + 2];
-                if (idx < trns.size()) px[3] = trns[idx];
-            } else if (channels <= 2) { // grey (+alpha): expanded to RGB (the reference indexes 3 channels regardless)
-                px[0] = px[1] = px[2] = sample8(x, 0);
-                if (channels == 2) px[3] = sample8(x, 1);
-            } else {
-                px[0] = sample8(x, 0), px[1] = sample8(x, 1), px[2] = sample8(x, 2);
-                if (channels == 4) px[3] = sample8(x, 3);
+            auto sample8 = [&](uint32_t x, int ch) -> uint8_t { // sample reduced to 8 bits the way stb_image's 8-bit API does
+                if (depth == 8) return cur[static_cast<size_t>(x) * channels + ch];
+                if (depth == 16) return cur[(static_cast<size_t>(x) * channels + ch) * 2]; // high byte
+                const size_t bit = static_cast<size_t>(x) * depth;
+                const uint8_t v = (cur[bit / 8] >> (8 - depth - bit % 8)) & ((1u << depth) - 1u);
+                return color == 3 ? v : static_cast<uint8_t>(v * (255 / ((1 << depth) - 1)));
+            };
+            for (uint32_t x = 0; x < pw; ++x) {
+                uint8_t px[4] = { 0, 0, 0, 255 };
+                if (color == 3) {
+                    const uint8_t idx = sample8(x, 0);
+                    if (static_cast<size_t>(idx) * 3 + 2 < palette.size()) px[0] = palette[idx * 3], px[1] = palette[idx * 3 + 1], px[2] = palette[idx * 3 + 2];
+                    if (idx < trns.size()) px[3] = trns[idx];
+                } else if (channels <= 2) { // grey (+alpha): expanded to RGB (the reference indexes 3 channels regardless)
+                    px[0] = px[1] = px[2] = sample8(x, 0);
+                    if (channels == 2) px[3] = sample8(x, 1);
+                } else {
+                    px[0] = sample8(x, 0), px[1] = sample8(x, 1), px[2] = sample8(x, 2);
+                    if (channels == 4) px[3] = sample8(x, 3);
+                }
+                float *o = &img.rgba[(static_cast<size_t>(ps.y0 + y * ps.dy) * w + ps.x0 + x * ps.dx) * 4];
+                o[0] = LdrToLinear(px[0]), o[1] = LdrToLinear(px[1]), o[2] = LdrToLinear(px[2]), o[3] = px[3] * 1.f / 255.f;
             }
-            float *o = &img.rgba[(static_cast<size_t>(y) * w + x) * 4];
-            o[0] = LdrToLinear(px[0]), o[1] = LdrToLinear(px[1]), o[2] = LdrToLinear(px[2]), o[3] = px[3] * 1.f / 255.f;
+            std::swap(prev, cur);
         }
-        std::swap(prev, cur);
+        src += ph * (stride + 1);
     }
     return true;
 }
@@ -598,7 +637,16 @@ bool LoadImage(std::string_view path, Image &out) noexcept {
         else if (file.size() >= 8 && file[0] == 0x89 && file[1] == 'P') ok = LoadPng(file, out);
         else if (file.size() >= 2 && file[0] == '#' && file[1] == '?') ok = LoadHdr(file, out);
         else if (file.size() >= 2 && file[0] == 'P' && (file[1] == 'F' || file[1] == 'f')) ok = LoadPfm(file, out);
-        else why = "unsupported format (hdr, exr, png and pfm are read)";
+        else {
+            ldr::Pixels8 px;
+            std::string ext = std::filesystem::path(std::string(path)).extension().string();
+            std::transform(ext.begin(), ext.end(), ext.begin(), [](unsigned char ch) { return static_cast<char>(std::tolower(ch)); });
+            if (file.size() >= 3 && file[0] == 0xff && file[1] == 0xd8 && file[2] == 0xff) ok = ldr::LoadJpeg(file.data(), file.size(), px, why);
+            else if (file.size() >= 2 && file[0] == 'B' && file[1] == 'M') ok = ldr::LoadBmp(file.data(), file.size(), px, why);
+            else if (ext == ".tga" && ldr::LooksLikeTga(file.data(), file.size())) ok = ldr::LoadTga(file.data(), file.size(), px, why); // no magic number
+            else why = "unsupported format (hdr, exr, png, jpeg, bmp, tga and pfm are read)";
+            if (ok) FromPixels8(px, out);
+        }
         if (!ok || !out.Valid()) {
             Log::Warn("fail to load image [%s]%s%s", std::string(path).c_str(), why.empty() ? "" : ": ", why.c_str());
             out = Image{};
