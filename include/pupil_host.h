@@ -47,6 +47,11 @@ int pupil_run(uint64_t n_pass_runs);
 int pupil_pass_state(uint32_t *sample_cnt, uint32_t *random_seed);
 
 /* BufferManager::GetBuffer(name): "final result", "pt accum buffer", "albedo", "normal", "test" */
+/* PTPass::SaveCheckpoint / LoadCheckpoint: the progressive state (accum + frame buffers, sample_cnt, random_seed, pass settings;
+ * pt_pass.cpp:55-56) to and from a file.  Load after the scene of the checkpoint was loaded; the run then continues with the
+ * same seeds and running mean, bit-identical to an uninterrupted one.  The reference has no checkpoint. */
+int pupil_checkpoint_save(const char *path);
+int pupil_checkpoint_load(const char *path);
 int pupil_buffer_info(const char *name, void **device_ptr, uint32_t *width, uint32_t *height, uint32_t *stride_in_byte);
 int pupil_buffer_download(const char *name, void *host, uint64_t bytes);
 int pupil_buffer_upload(const char *name, const void *host, uint64_t bytes);

@@ -155,6 +155,14 @@ int pupil_pass_state(uint32_t *sample_cnt, uint32_t *random_seed) {
     if (random_seed) *random_seed = g_pass->GetLaunchParams().random_seed;
     return 0;
 }
+int pupil_checkpoint_save(const char *path) {
+    if (!Ready() || !path) return Fail("pupil_init first");
+    return g_pass->SaveCheckpoint(path) ? 0 : Fail(std::string("cannot save checkpoint: ") + path);
+}
+int pupil_checkpoint_load(const char *path) {
+    if (!Ready() || !path) return Fail("pupil_init first");
+    return g_pass->LoadCheckpoint(path) ? 0 : Fail(std::string("cannot load checkpoint: ") + path);
+}
 int pupil_buffer_info(const char *name, void **dptr, uint32_t *w, uint32_t *h, uint32_t *stride) {
     Buffer *b = name ? util::Singleton<BufferManager>::instance()->GetBuffer(name) : nullptr;
     if (!b) return Fail(std::string("no buffer named ") + (name ? name : "(null)"));

@@ -1,6 +1,9 @@
 #include "pt_pass.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <vector>
 
 namespace Pupil::pt {
 namespace {
@@ -107,6 +110,105 @@ void PTPass::Restart(unsigned int first_seed, unsigned int seed_stride) noexcept
     m_first_seed = first_seed, m_seed_stride = seed_stride ? seed_stride : 1;
     m_dirty = true;
 }
+namespace {
+struct CheckpointHeader { // little-endian, 64 bytes
+    char magic[8];        // "PB2CKPT1"
+    uint32_t width, height, max_depth, accumulate, sum_mode;
+    uint32_t sample_cnt, random_seed, first_seed, seed_stride, frames_per_run;
+    uint32_t reserved[4];
+};
+static_assert(sizeof(CheckpointHeader) == 64);
+constexpr char kCheckpointMagic[8] = { 'P', 'B', '2', 'C', 'K', 'P', 'T', '1' };
+}// namespace
+
+bool PTPass::SaveCheckpoint(const std::filesystem::path &file) noexcept {
+    try {
+        if (!m_world || !m_params.accum_buffer || !m_params.frame_buffer) {
+            Log::Warn("checkpoint: no scene to save");
+            return false;
+        }
+        if (m_params.handle) pb2_synchronize(m_params.handle);
+        CheckpointHeader h{};
+        std::memcpy(h.magic, kCheckpointMagic, 8);
+        h.width = m_params.config.frame.width, h.height = m_params.config.frame.height;
+        // a pending reset (m_dirty) has not reached m_params yet: a checkpoint taken then describes a pass that starts over
+        h.max_depth = m_dirty ? static_cast<uint32_t>(m_max_depth) : m_params.config.max_depth;
+        h.accumulate = (m_dirty ? m_accumulated_flag : m_params.config.accumulated_flag) ? 1u : 0u;
+        h.sum_mode = m_sum_mode ? 1u : 0u;
+        h.sample_cnt = m_dirty ? 0u : m_params.sample_cnt, h.random_seed = m_dirty ? m_first_seed : m_params.random_seed;
+        h.first_seed = m_first_seed, h.seed_stride = m_seed_stride, h.frames_per_run = m_frames_per_run;
+        std::vector<float> accum(m_output_pixel_num * 4), frame(m_output_pixel_num * 4);
+        if (pb2_download(accum.data(), m_params.accum_buffer, accum.size() * sizeof(float)) != PB2_OK ||
+            pb2_download(frame.data(), m_params.frame_buffer, frame.size() * sizeof(float)) != PB2_OK) {
+            Log::Error("checkpoint: %s", pb2_last_error());
+            return false;
+        }
+        // written under a temporary name and renamed: a run killed while saving leaves the previous checkpoint intact
+        const std::filesystem::path tmp = file.string() + ".tmp";
+        std::FILE *f = std::fopen(tmp.string().c_str(), "wb");
+        if (!f) {
+            Log::Warn("checkpoint: cannot write %s", tmp.string().c_str());
+            return false;
+        }
+        bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(accum.data(), sizeof(float), accum.size(), f) == accum.size() &&
+                  std::fwrite(frame.data(), sizeof(float), frame.size(), f) == frame.size();
+        ok = std::fclose(f) == 0 && ok;
+        std::error_code ec;
+        if (ok) std::filesystem::rename(tmp, file, ec);
+        if (!ok || ec) {
+            Log::Warn("checkpoint: cannot write %s", file.string().c_str());
+            std::filesystem::remove(tmp, ec);
+            return false;
+        }
+        return true;
+    } catch (...) {
+        return false;
+    }
+}
+
+bool PTPass::LoadCheckpoint(const std::filesystem::path &file) noexcept {
+    try {
+        if (!m_world || !m_params.accum_buffer || !m_params.frame_buffer) {
+            Log::Warn("checkpoint: set the scene before loading a checkpoint");
+            return false;
+        }
+        std::FILE *f = std::fopen(file.string().c_str(), "rb");
+        if (!f) {
+            Log::Warn("checkpoint: cannot read %s", file.string().c_str());
+            return false;
+        }
+        CheckpointHeader h{};
+        std::vector<float> accum(m_output_pixel_num * 4), frame(m_output_pixel_num * 4);
+        bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, kCheckpointMagic, 8) == 0;
+        if (ok && (h.width != m_params.config.frame.width || h.height != m_params.config.frame.height)) {
+            Log::Warn("checkpoint: %s holds a %ux%u frame, the scene renders %ux%u", file.string().c_str(), h.width, h.height, m_params.config.frame.width,
+                      m_params.config.frame.height);
+            ok = false;
+        }
+        ok = ok && std::fread(accum.data(), sizeof(float), accum.size(), f) == accum.size() && std::fread(frame.data(), sizeof(float), frame.size(), f) == frame.size();
+        ok = ok && std::fgetc(f) == EOF; // nothing may follow
+        std::fclose(f);
+        if (!ok) {
+            Log::Warn("checkpoint: %s is not a checkpoint of this scene", file.string().c_str());
+            return false;
+        }
+        if (m_params.handle) pb2_synchronize(m_params.handle);
+        if (pb2_upload(m_params.accum_buffer, accum.data(), accum.size() * sizeof(float)) != PB2_OK ||
+            pb2_upload(m_params.frame_buffer, frame.data(), frame.size() * sizeof(float)) != PB2_OK) {
+            Log::Error("checkpoint: %s", pb2_last_error());
+            return false;
+        }
+        m_max_depth = std::clamp(static_cast<int>(h.max_depth), 1, 128), m_accumulated_flag = h.accumulate != 0, m_sum_mode = h.sum_mode != 0;
+        m_first_seed = h.first_seed, m_seed_stride = h.seed_stride ? h.seed_stride : 1, m_frames_per_run = h.frames_per_run ? h.frames_per_run : 1;
+        m_params.config.max_depth = m_max_depth, m_params.config.accumulated_flag = m_accumulated_flag;
+        m_params.sample_cnt = h.sample_cnt, m_params.random_seed = h.random_seed;
+        m_dirty = false; // the next OnRun continues instead of starting over
+        return true;
+    } catch (...) {
+        return false;
+    }
+}
+
 pb2_render_stats PTPass::GetRenderStats() noexcept {
     pb2_render_stats st{};
     if (m_params.handle) pb2_render_stats_get(m_params.handle, &st);

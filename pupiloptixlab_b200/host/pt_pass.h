@@ -9,6 +9,7 @@
 #include "system.h"
 
 #include <atomic>
+#include <filesystem>
 
 namespace Pupil::pt {
 // pt::OptixLaunchParams (type.h:9-33): camera, emitter group and the AS handle live in the pb2 scene
@@ -40,6 +41,12 @@ public:
     void SetFramesPerRun(unsigned int n) noexcept { m_frames_per_run = n ? n : 1; }
     // restart the progressive sequence at a given seed without touching the scene (checkpoint / shard support)
     void Restart(unsigned int first_seed = 0, unsigned int seed_stride = 1) noexcept;
+    // Checkpoint of the progressive state — the reference has none; its state is (accum buffer, sample_cnt,
+    // random_seed) (pt_pass.cpp:55-56), which is what the file holds next to the frame size and the pass settings.  A pass
+    // resumed from a checkpoint of the same scene continues with the same seeds and the same running mean: the images are
+    // bit-identical to an uninterrupted run.  Load wants the scene of the checkpoint set first (frame size is checked).
+    bool SaveCheckpoint(const std::filesystem::path &file) noexcept;
+    bool LoadCheckpoint(const std::filesystem::path &file) noexcept;
     void SetSumMode(bool sum) noexcept { m_sum_mode = sum, m_dirty = true; } // accumulate plain sums (multi-GPU shards)
     const LaunchParams &GetLaunchParams() const noexcept { return m_params; }
     pb2_render_stats GetRenderStats() noexcept;

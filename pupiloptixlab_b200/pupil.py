@@ -56,6 +56,7 @@ def lib():
             "pupil_register_image": [C.c_char_p, vp, u32, u32], "pupil_image_load": [C.c_char_p, P(u32), P(u32), vp, u64],
             "pupil_image_save": [C.c_char_p, vp, u32, u32, C.c_int], "pupil_save_buffer": [C.c_char_p, C.c_char_p, C.c_int],
             "pupil_get_env_tables": [P(u32), P(u32), vp, vp, vp], "pupil_set_instance_transform": [u32, P(f32)],
+            "pupil_checkpoint_save": [C.c_char_p], "pupil_checkpoint_load": [C.c_char_p],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -162,6 +163,16 @@ def pass_config(max_depth: int = 0, accumulate: bool = True, frames_per_run: int
 
 def run(n_pass_runs: int = 1):
     check(lib().pupil_run(n_pass_runs))
+
+
+def checkpoint_save(path):
+    """PTPass::SaveCheckpoint: accum + frame buffers, sample count, next seed, pass settings"""
+    check(lib().pupil_checkpoint_save(str(path).encode()))
+
+
+def checkpoint_load(path):
+    """PTPass::LoadCheckpoint (the checkpoint's scene must be loaded): the next run() continues where the checkpoint stopped"""
+    check(lib().pupil_checkpoint_load(str(path).encode()))
 
 
 def pass_state():

@@ -273,3 +273,58 @@ def test_reference_xml_through_path_tracer_binary(tmp_path):
     assert raw.startswith(b"PF\n64 64\n-1.0\n")
     img = np.frombuffer(raw[len(b"PF\n64 64\n-1.0\n"):], np.float32).reshape(64, 64, 3)
     assert np.isfinite(img).all() and 0.05 < img.mean() < 1.0
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    """progressive state (accum, frame, sample_cnt, random_seed) saved after 5 frames, the system torn down, the scene loaded
+    again, the checkpoint loaded, 7 more frames: the same buffers as 12 uninterrupted frames, bit for bit"""
+    desc = scenes.material_grid(96, 54, 6)
+    pupil.load_scene(desc)
+    pupil.pass_config(frames_per_run=1)
+    pupil.run(12)
+    want_accum, want_frame = pupil.buffer("pt accum buffer").copy(), pupil.buffer("final result").copy()
+    pupil.pass_config(frames_per_run=1)
+    pupil.run(5)
+    ck = tmp_path / "state.ckpt"
+    pupil.checkpoint_save(ck)
+    assert ck.stat().st_size == 64 + 2 * 96 * 54 * 16 and not (tmp_path / "state.ckpt.tmp").exists()
+    pupil.shutdown()
+    pupil.init(0)
+    pupil.load_scene(desc)
+    pupil.checkpoint_load(ck)
+    assert pupil.pass_state() == (5, 5)
+    pupil.run(7)
+    assert pupil.pass_state() == (12, 12)
+    assert np.array_equal(want_accum, pupil.buffer("pt accum buffer")) and np.array_equal(want_frame, pupil.buffer("final result"))
+    # a checkpoint of another frame size, a truncated one and a missing one are refused, and the pass state stays as it was
+    pupil.load_scene(scenes.cornell_box(32, 32, 4))
+    pupil.pass_config()
+    pupil.run(2)
+    for bad in (ck, tmp_path / "missing.ckpt"):
+        with pytest.raises(pupil.PupilError):
+            pupil.checkpoint_load(bad)
+    small = tmp_path / "small.ckpt"
+    pupil.checkpoint_save(small)
+    small.write_bytes(small.read_bytes()[:-8])
+    with pytest.raises(pupil.PupilError):
+        pupil.checkpoint_load(small)
+    assert pupil.pass_state() == (2, 2)
+
+
+def test_path_tracer_binary_checkpoint_and_resume(tmp_path):
+    """path_tracer --checkpoint / --resume: 4 + 4 spp in two processes write the same picture as 8 spp in one"""
+    import subprocess
+    from pupiloptixlab_b200 import pb2
+    xml = scenes.to_xml(scenes.cornell_box(48, 48, 5), tmp_path / "cb.xml")
+    exe = str(pb2.PKG / "_build" / "path_tracer")
+    run = lambda *a: subprocess.run([exe, "--scene", str(xml), *a], capture_output=True, text=True)  # noqa: E731
+    r = run("--spp", "8", "--batch", "4", "--out", str(tmp_path / "full.pfm"))
+    assert r.returncode == 0, r.stderr
+    r = run("--spp", "4", "--batch", "4", "--out", str(tmp_path / "half.pfm"), "--checkpoint", str(tmp_path / "s.ckpt"))
+    assert r.returncode == 0, r.stderr
+    r = run("--spp", "8", "--batch", "4", "--out", str(tmp_path / "resumed.pfm"), "--resume", str(tmp_path / "s.ckpt"))
+    assert r.returncode == 0 and "resumed at 4 spp" in r.stdout, r.stderr
+    assert (tmp_path / "full.pfm").read_bytes() == (tmp_path / "resumed.pfm").read_bytes()
+    assert (tmp_path / "full.pfm").read_bytes() != (tmp_path / "half.pfm").read_bytes()
+    r = run("--spp", "8", "--resume", str(tmp_path / "nope.ckpt"))
+    assert r.returncode == 1
