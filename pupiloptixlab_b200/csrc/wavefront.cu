@@ -475,10 +475,17 @@ __global__ void __launch_bounds__(256) k_bin(SceneView sv, PathArrays pa, const 
 // Order-preserving append of a 128-thread CTA to two queues at once: thread order is kept inside the CTA's slice
 // (a CTA works on 128 consecutive queue entries, so runs of ascending path slots survive compaction and the next
 // kernel's record accesses stay close to sequential), one atomic per queue per CTA.
+#ifndef PB2_SHADE_WAVES
+#define PB2_SHADE_WAVES 2
+#endif
+#ifndef PB2_SHADE_THREADS
+#define PB2_SHADE_THREADS 128
+#endif
+constexpr uint32_t kShadeThreads = PB2_SHADE_THREADS, kShadeWarps = kShadeThreads / 32, kShadeMask = kShadeThreads - 1;
 __device__ __forceinline__ void block_append2(uint32_t *counter_a, uint32_t *counter_b, bool pred_a, bool pred_b, uint32_t &pos_a, uint32_t &pos_b, uint32_t parity) {
     // two copies of the scratch words, used alternately by successive calls (`parity`): the next call writes the other copy
     // and the call after that is two barriers away, so no third barrier is needed to protect the reads below
-    __shared__ uint32_t s_cnt[2][2][4], s_base[2][2];
+    __shared__ uint32_t s_cnt[2][2][kShadeWarps], s_base[2][2];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, b = parity & 1u;
     const uint32_t ma = __ballot_sync(0xffffffffu, pred_a), mb = __ballot_sync(0xffffffffu, pred_b);
     if (lane == 0) s_cnt[b][0][warp] = __popc(ma), s_cnt[b][1][warp] = __popc(mb);
@@ -486,7 +493,7 @@ __device__ __forceinline__ void block_append2(uint32_t *counter_a, uint32_t *cou
     if (threadIdx.x < 2) {
         uint32_t run = 0;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < (int)kShadeWarps; ++w) {
             const uint32_t c = s_cnt[b][threadIdx.x][w];
             s_cnt[b][threadIdx.x][w] = run;
             run += c;
@@ -504,15 +511,16 @@ __device__ __forceinline__ void block_append2(uint32_t *counter_a, uint32_t *cou
 // range [start_t, start_t + round_up(count_t, 128)): a CTA never straddles two material types); otherwise the
 // kernel walks the extension queue itself, in order, and branches on the material per path.
 template<int MINB, bool SORTED>
-__global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa, FrameParams fp, const uint32_t *__restrict__ queue,
+__global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_shade(SceneView sv, PathArrays pa, FrameParams fp, const uint32_t *__restrict__ queue,
                                                const uint32_t *__restrict__ counts, uint32_t capacity, ShadeOut out) {
     uint32_t start[kNumTypes + 1];
     start[0] = 0;
     if (SORTED) {
 #pragma unroll
-        for (int t = 0; t < kNumTypes; ++t) start[t + 1] = start[t] + ((counts[t] + 127u) & ~127u);
+        for (int t = 0; t < kNumTypes; ++t) start[t + 1] = start[t] + ((counts[t] + kShadeMask) & ~kShadeMask);
     }
-    const uint32_t total = SORTED ? start[kNumTypes] : ((counts[0] + 127u) & ~127u);
+    const uint32_t n_unsorted = SORTED ? 0u : counts[0]; // read once: the loop below would reload it from memory every iteration
+    const uint32_t total = SORTED ? start[kNumTypes] : ((n_unsorted + kShadeMask) & ~kShadeMask);
 
     // queue entry of virtual index vi (SORTED: the eight material queues laid end to end, each padded to 128)
     auto fetch = [&](uint32_t vi, uint32_t &p) -> bool {
@@ -524,7 +532,7 @@ __global__ void __launch_bounds__(128, MINB) k_shade(SceneView sv, PathArrays pa
             if (local >= counts[t]) return false;
             p = queue[(size_t)t * capacity + local];
         } else {
-            if (vi >= counts[0]) return false;
+            if (vi >= n_unsorted) return false;
             p = queue[vi];
         }
         return true;
@@ -693,8 +701,8 @@ void render(Scene &s, const pb2_launch_params &lp) {
                         lp.seed_stride ? lp.seed_stride : 1u, frames };
         const unsigned grid_stream = (unsigned)std::min<uint64_t>((n_paths + 255) / 256, (uint64_t)sms * 8);
         const unsigned grid_trace = (unsigned)std::min<uint64_t>((n_paths + 127) / 128, (uint64_t)sms * 16);
-        const unsigned grid_shade = (unsigned)std::min<uint64_t>((n_paths + kNumTypes * 128 + 127) / 128,
-                                                                   (uint64_t)sms * 2 * (s.shade_variant >= 4 && s.shade_variant <= 8 ? s.shade_variant : 6)); // two full waves of resident CTAs
+        const unsigned grid_shade = (unsigned)std::min<uint64_t>((n_paths + kNumTypes * kShadeThreads + kShadeMask) / kShadeThreads,
+                                                                   (uint64_t)sms * PB2_SHADE_WAVES * (s.shade_variant >= 4 && s.shade_variant <= 8 ? s.shade_variant : 6) * 128 / kShadeThreads); // full waves of resident CTAs
 
         // the second lane starts one kernel late, so that its trace kernels meet the first lane's shade kernels rather
         // than both lanes running the same stage side by side
@@ -732,17 +740,17 @@ void render(Scene &s, const pb2_launch_params &lp) {
             stage_begin(2);
             if (sorted) {
                 switch (s.shade_variant) {
-                    case 4: k_shade<4, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
-                    case 7: k_shade<7, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
-                    case 8: k_shade<8, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
-                    default: k_shade<6, true><<<grid_shade, 128, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
+                    case 4: k_shade<4, true><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
+                    case 7: k_shade<7, true><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
+                    case 8: k_shade<8, true><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
+                    default: k_shade<6, true><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
                 }
             } else {
                 switch (s.shade_variant) {
-                    case 4: k_shade<4, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
-                    case 7: k_shade<7, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
-                    case 8: k_shade<8, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
-                    default: k_shade<6, false><<<grid_shade, 128, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
+                    case 4: k_shade<4, false><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
+                    case 7: k_shade<7, false><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
+                    case 8: k_shade<8, false><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
+                    default: k_shade<6, false><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, q_in, ctr + CTR_EXT, (uint32_t)ln.capacity, so); break;
                 }
             }
             PB2_LAUNCH_CHECK();
