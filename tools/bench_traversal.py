@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--refill", type=str, default="", help="comma list of refill thresholds to sweep")
     ap.add_argument("--orders", action="store_true", help="also trace the incoherent batch in three coherent orders")
+    ap.add_argument("--big", type=int, default=0, help="also trace this many incoherent / shadow rays in one launch (origins resampled with replacement): "
+                    "the 2^21-ray batches of config C4 give each resident warp ~200 rays, so ramp-up and tail are a visible share of the launch")
     ap.add_argument("--l2", type=str, default="", help="comma list of persist_mb:window_mb pairs for the L2 access-policy window over the top of the node array")
     ap.add_argument("--coop", type=int, default=-1, help="warp-cooperative primitive tests: 1 on, 0 off, -1 auto")
     args = ap.parse_args()
@@ -167,6 +169,22 @@ def main():
         if thr is not None:
             apply(thr)
         trace(sh, True, f"anyhit_shadow_to_light thr={thr}")
+    if args.big:
+        kb = args.big
+        selb = rng.integers(0, len(pos), kb)
+        pb = pos[selb]
+        u1, u2 = rng.random(kb, dtype=np.float32), rng.random(kb, dtype=np.float32)
+        rr, ph = np.sqrt(u1), 2 * np.pi * u2
+        big = np.zeros((kb, 8), np.float32)
+        big[:, 0:3], big[:, 3], big[:, 7] = pb, 1e-3, 1e16
+        big[:, 4], big[:, 5], big[:, 6] = rr * np.cos(ph), np.sqrt(np.maximum(0, 1 - u1)), rr * np.sin(ph)
+        trace(big, False, f"closest_incoherent_bounce {kb} rays")
+        lb = np.array([0.0, 12.0, 0.0], np.float32) + rng.uniform(-3, 3, (kb, 3)).astype(np.float32) * np.array([1, 0, 1], np.float32)
+        dlb = lb - pb
+        db = np.linalg.norm(dlb, axis=1, keepdims=True)
+        big[:, 3], big[:, 4:7], big[:, 7] = 1e-4, dlb / db, db[:, 0] - 1e-4
+        trace(big, True, f"anyhit_shadow_to_light {kb} rays")
+        del big
     for pair in [x for x in args.l2.split(",") if x]:
         persist, window = (int(y) for y in pair.split(":"))
         scene.set_option("l2_persist_mb", persist)
