@@ -119,34 +119,36 @@ struct Component {
 // column pass keeps 2 extra bits (>> 10 after + 512), the row pass removes 17 with the rounding term and the + 128 level
 // shift folded into one bias.  Following those rules makes the texels equal to the reference's.
 constexpr int Fx(float x) { return static_cast<int>(x * 4096 + 0.5); }
+// (64-bit intermediates: corrupt files can carry coefficients that overflow 32 bits; valid ones give the same values either way)
+using I64 = long long;
 struct Lm8 {
-    int even[4], odd[4]; // out[k] = even[k] + odd[3 - k], out[7 - k] = even[k] - odd[3 - k]
+    I64 even[4], odd[4]; // out[k] = even[k] + odd[3 - k], out[7 - k] = even[k] - odd[3 - k]
 };
-inline Lm8 LmButterfly(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7, int bias) {
+inline Lm8 LmButterfly(I64 s0, I64 s1, I64 s2, I64 s3, I64 s4, I64 s5, I64 s6, I64 s7, I64 bias) {
     Lm8 r;
-    const int z = (s2 + s6) * Fx(0.5411961f);
-    const int a2 = z + s6 * Fx(-1.847759065f), a3 = z + s2 * Fx(0.765366865f);
-    const int a0 = (s0 + s4) * 4096 + bias, a1 = (s0 - s4) * 4096 + bias;
+    const I64 z = (s2 + s6) * Fx(0.5411961f);
+    const I64 a2 = z + s6 * Fx(-1.847759065f), a3 = z + s2 * Fx(0.765366865f);
+    const I64 a0 = (s0 + s4) * 4096 + bias, a1 = (s0 - s4) * 4096 + bias;
     r.even[0] = a0 + a3, r.even[3] = a0 - a3, r.even[1] = a1 + a2, r.even[2] = a1 - a2;
-    const int q3 = s7 + s3, q4 = s5 + s1, q1 = s7 + s1, q2 = s5 + s3;
-    const int q5 = (q3 + q4) * Fx(1.175875602f);
-    const int m1 = q5 + q1 * Fx(-0.899976223f), m2 = q5 + q2 * Fx(-2.562915447f);
-    const int m3 = q3 * Fx(-1.961570560f), m4 = q4 * Fx(-0.390180644f);
+    const I64 q3 = s7 + s3, q4 = s5 + s1, q1 = s7 + s1, q2 = s5 + s3;
+    const I64 q5 = (q3 + q4) * Fx(1.175875602f);
+    const I64 m1 = q5 + q1 * Fx(-0.899976223f), m2 = q5 + q2 * Fx(-2.562915447f);
+    const I64 m3 = q3 * Fx(-1.961570560f), m4 = q4 * Fx(-0.390180644f);
     r.odd[0] = s7 * Fx(0.298631336f) + m1 + m3;
     r.odd[1] = s5 * Fx(2.053119869f) + m2 + m4;
     r.odd[2] = s3 * Fx(3.072711026f) + m2 + m3;
     r.odd[3] = s1 * Fx(1.501321110f) + m1 + m4;
     return r;
 }
-inline uint8_t Clamp8(int x) { return static_cast<uint8_t>(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+inline uint8_t Clamp8(I64 x) { return static_cast<uint8_t>(x < 0 ? 0 : (x > 255 ? 255 : x)); }
 void InverseDct(const int16_t *c, uint8_t *out, int stride) {
-    int tmp[64];
+    I64 tmp[64];
     for (int x = 0; x < 8; ++x) {
         const Lm8 r = LmButterfly(c[x], c[8 + x], c[16 + x], c[24 + x], c[32 + x], c[40 + x], c[48 + x], c[56 + x], 512);
         for (int k = 0; k < 4; ++k) tmp[k * 8 + x] = (r.even[k] + r.odd[3 - k]) >> 10, tmp[(7 - k) * 8 + x] = (r.even[k] - r.odd[3 - k]) >> 10;
     }
     for (int y = 0; y < 8; ++y) {
-        const int *t = tmp + y * 8;
+        const I64 *t = tmp + y * 8;
         const Lm8 r = LmButterfly(t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], 65536 + (128 << 17));
         uint8_t *o = out + y * stride;
         for (int k = 0; k < 4; ++k) o[k] = Clamp8((r.even[k] + r.odd[3 - k]) >> 17), o[7 - k] = Clamp8((r.even[k] - r.odd[3 - k]) >> 17);
@@ -717,9 +719,12 @@ bool LoadTga(const uint8_t *file, size_t n, Pixels8 &out, std::string &why) {
             if (channels == 2) o[1] = s[1];
         }
     };
-    out.w = w, out.h = h, out.channels = channels;
-    out.data.assign(static_cast<size_t>(w) * h * channels, 0);
     const size_t elem = cmap ? idx_bytes : src_bytes, total = static_cast<size_t>(w) * h;
+    // the header alone must not be able to ask for gigabytes: raw pixels need their bytes, a run-length packet (1 + elem bytes)
+    // expands to at most 128 pixels
+    if (pos > n || (!rle && (n - pos) / elem < total) || (rle && ((n - pos) / (1 + elem) + 1) * 128 < total)) return fail("truncated pixel data");
+    out.w = w, out.h = h, out.channels = channels;
+    out.data.assign(total * channels, 0);
     uint8_t px[4] = { 0, 0, 0, 0 };
     auto read_elem = [&]() -> bool {
         if (pos + elem > n) return false;
