@@ -277,6 +277,9 @@ bool LoadPng(const std::vector<uint8_t> &file, Image &img) {
     size_t raw_size = 0;
     for (int i = 0; i < n_passes; ++i)
         if (pass_w(passes[i]) && pass_h(passes[i])) raw_size += pass_h(passes[i]) * (stride_of(pass_w(passes[i])) + 1);
+    // deflate expands by at most ~1032 : 1, so a header that promises more than the IDAT bytes can hold is corrupt (and must not
+    // be able to ask for gigabytes)
+    if (static_cast<uint64_t>(w) * h > (1ull << 28) || raw_size > idat.size() * 1040 + 64) return false;
     std::vector<uint8_t> raw(raw_size);
     uLongf raw_len = static_cast<uLongf>(raw.size());
     if (uncompress(raw.data(), &raw_len, idat.data(), static_cast<uLong>(idat.size())) != Z_OK || raw_len != raw.size()) return false;

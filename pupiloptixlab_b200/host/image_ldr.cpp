@@ -194,6 +194,11 @@ struct JpegDecoder {
         for (int i = 0; i < n_comp; ++i)
             if (h_max % comp[i].h || v_max % comp[i].v) return Fail("fractional sampling ratios are not read");
         mcus_x = (width + 8 * h_max - 1) / (8 * h_max), mcus_y = (height + 8 * v_max - 1) / (8 * v_max);
+        // every coded block costs at least one bit, so a header that promises more blocks than the file has bits is corrupt
+        // (and must not be able to ask for gigabytes of coefficient storage)
+        uint64_t blocks_total = 0;
+        for (int i = 0; i < n_comp; ++i) blocks_total += static_cast<uint64_t>(mcus_x) * comp[i].h * mcus_y * comp[i].v;
+        if (blocks_total > static_cast<uint64_t>(size) * 8) return Fail("frame larger than its data");
         for (int i = 0; i < n_comp; ++i) {
             Component &c = comp[i];
             c.blocks_w = mcus_x * c.h, c.blocks_h = mcus_y * c.v;
