@@ -459,6 +459,9 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
     for (auto &c : channels) line_bytes += c.bytes() * w;
     // channel -> RGBA slot; a single channel (luminance) is replicated like tinyexr's LoadEXR does
     auto slot_of = [&](const std::string &n) { return n == "R" ? 0 : n == "G" ? 1 : n == "B" ? 2 : n == "A" ? 3 : -1; };
+    // the offset table must fit, and zlib / RLE expand by at most ~1032 : 1: a data window the file's bytes cannot fill is corrupt
+    // (and must not be able to ask for gigabytes)
+    if (!r.ok || dw[2] < dw[0] || dw[3] < dw[1] || w > (1u << 20) || h > (1u << 20) || w * h > (size_t(1) << 28) || line_bytes * h > file.size() * 1040 + 64) return false;
     img.w = w, img.h = h;
     img.rgba.assign(w * h * 4, 0.f);
     for (size_t i = 0; i < w * h; ++i) img.rgba[i * 4 + 3] = 1.f;
