@@ -106,6 +106,8 @@ void Scene::upload_tables() {
     uint32_t seen = 0;
     for (const DevInstance &in : h_inst) seen |= 1u << (in.mat_type & 7);
     n_material_types = __builtin_popcount(seen);
+    only_material_type = n_material_types == 1 ? __builtin_ctz(seen) : -1;
+    material_type_mask = seen;
     d_inst.upload(h_inst.data(), h_inst.size(), stream);
     d_mat.upload(h_mat.data(), h_mat.size(), stream);
     d_areas.upload(h_areas.data(), h_areas.size(), stream);

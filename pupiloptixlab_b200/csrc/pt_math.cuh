@@ -207,11 +207,13 @@ struct LocalBsdf {
     float3 c0, c1, c2;
 };
 // Material::GetLocalBsdf, render/material/optix_material.h:117-130
-PB2_D LocalBsdf get_local_bsdf(const DevMaterial *m, float2 uv) {
+// forced_type >= 0: the caller knows every material of the scene has this type (a compile-time constant there), so the switches
+// here and in bsdf_sample / bsdf_eval fold to one case
+PB2_D LocalBsdf get_local_bsdf(const DevMaterial *m, float2 uv, int forced_type = -1) {
     LocalBsdf b;
     const int4 h0 = __ldg(reinterpret_cast<const int4 *>(m));
     const float2 h1 = __ldg(reinterpret_cast<const float2 *>(m) + 2);
-    b.type = h0.x;
+    b.type = forced_type >= 0 ? forced_type : h0.x;
     b.eta = __int_as_float(h0.z);
     b.nonlinear = h0.w != 0;
     b.int_fdr = h1.x, b.specular_sampling_weight = h1.y;

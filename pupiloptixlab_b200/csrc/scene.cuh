@@ -44,6 +44,8 @@ struct Scene {
     bool profiling = false, counting = false;
     int sort_by_material = -1;  // 1 on, 0 off, -1 auto (on when the scene has more than one material type)
     int n_material_types = 0;   // distinct EMatType values among the instances (upload_tables)
+    int only_material_type = -1; // that type when there is exactly one, else -1
+    uint32_t material_type_mask = 0; // bit t: some instance has material type t
     uint64_t paths_in_flight = 0;
     int refill_threshold = 26;
     int shade_variant = 6;     // k_shade<MINB>: 4, 6, 7 or 8 resident CTAs per SM

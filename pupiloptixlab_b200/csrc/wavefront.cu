@@ -302,6 +302,8 @@ struct ShadowRay {
     float tmax;
 };
 // One path at one hit (or miss).  Returns bit 0: `sh` holds a shadow ray, bit 1: an extension ray was written.
+// ONLY >= 0: every instance of the scene has this material type (Scene::only_material_type), the other six BSDFs are compiled out
+template<int ONLY>
 __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathArrays &pa, const FrameParams &fp, const ShadeOut &out, uint32_t p, ShadowRay &sh) {
     const float4 hit = pa.hit[p]; // u, v (triangle) or t (sphere), prim, inst
     const int32_t inst = __float_as_int(hit.w);
@@ -344,6 +346,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
         add_radiance();
         return 0u;
     }
+    if (ONLY == 0) return 0u; // the miss queue of the sorted mode holds nothing else
 
     // __closesthit__default, main.cu:220-234
     const DevInstance *in = sv.instances + inst;
@@ -353,7 +356,7 @@ __device__ __forceinline__ uint32_t shade_path(const SceneView &sv, const PathAr
     LocalGeometry geo;
     hit_local_geometry(in, flags, ray_o, ray_d, hit.x, hit.x, hit.y, prim, geo);
     const int emitter_index = (int)meta.z >= 0 ? (int)meta.z + (int)prim : -1;
-    const LocalBsdf bsdf = get_local_bsdf(sv.materials + inst, geo.texcoord);
+    const LocalBsdf bsdf = get_local_bsdf(sv.materials + inst, geo.texcoord, ONLY);
 
     if (depth == 0) { // :90-104
         if (emitter_index >= 0) radiance += emitter_radiance(sv.areas + emitter_index, geo.texcoord);
@@ -475,6 +478,9 @@ __global__ void __launch_bounds__(256) k_bin(SceneView sv, PathArrays pa, const 
 // Order-preserving append of a 128-thread CTA to two queues at once: thread order is kept inside the CTA's slice
 // (a CTA works on 128 consecutive queue entries, so runs of ascending path slots survive compaction and the next
 // kernel's record accesses stay close to sequential), one atomic per queue per CTA.
+#ifndef PB2_SHADE_PER_TYPE
+#define PB2_SHADE_PER_TYPE 1
+#endif
 #ifndef PB2_SHADE_WAVES
 #define PB2_SHADE_WAVES 2
 #endif
@@ -510,21 +516,25 @@ __device__ __forceinline__ void block_append2(uint32_t *counter_a, uint32_t *cou
 // SORTED: paths come from the eight per-material queues filled by k_extend (queue t occupies the virtual index
 // range [start_t, start_t + round_up(count_t, 128)): a CTA never straddles two material types); otherwise the
 // kernel walks the extension queue itself, in order, and branches on the material per path.
-template<int MINB, bool SORTED>
+template<int MINB, bool SORTED, int ONLY = -1>
 __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_shade(SceneView sv, PathArrays pa, FrameParams fp, const uint32_t *__restrict__ queue,
                                                const uint32_t *__restrict__ counts, uint32_t capacity, ShadeOut out) {
+    // MULTI: all eight material queues in one launch (SORTED with ONLY < 0, kept for A/B runs); otherwise one queue — the
+    // extension queue itself (unsorted), or material queue ONLY of the sorted mode, one launch per material type of the scene
+    constexpr bool MULTI = SORTED && ONLY < 0;
     uint32_t start[kNumTypes + 1];
     start[0] = 0;
-    if (SORTED) {
+    if (MULTI) {
 #pragma unroll
         for (int t = 0; t < kNumTypes; ++t) start[t + 1] = start[t] + ((counts[t] + kShadeMask) & ~kShadeMask);
     }
-    const uint32_t n_unsorted = SORTED ? 0u : counts[0]; // read once: the loop below would reload it from memory every iteration
-    const uint32_t total = SORTED ? start[kNumTypes] : ((n_unsorted + kShadeMask) & ~kShadeMask);
+    if (SORTED && !MULTI) queue += (size_t)ONLY * capacity;
+    const uint32_t n_single = MULTI ? 0u : counts[SORTED ? ONLY : 0]; // read once: the loop below would reload it from memory every iteration
+    const uint32_t total = MULTI ? start[kNumTypes] : ((n_single + kShadeMask) & ~kShadeMask);
 
-    // queue entry of virtual index vi (SORTED: the eight material queues laid end to end, each padded to 128)
+    // queue entry of virtual index vi (MULTI: the eight material queues laid end to end, each padded to 128)
     auto fetch = [&](uint32_t vi, uint32_t &p) -> bool {
-        if (SORTED) {
+        if (MULTI) {
             int t = 0;
 #pragma unroll
             for (int k = 1; k < kNumTypes; ++k) t += vi >= start[k] ? 1 : 0;
@@ -532,7 +542,7 @@ __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_s
             if (local >= counts[t]) return false;
             p = queue[(size_t)t * capacity + local];
         } else {
-            if (vi >= n_unsorted) return false;
+            if (vi >= n_single) return false;
             p = queue[vi];
         }
         return true;
@@ -559,7 +569,7 @@ __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_s
         }
 #endif
 #endif
-        if (valid) emitted = shade_path(sv, pa, fp, out, p, sh);
+        if (valid) emitted = shade_path<ONLY>(sv, pa, fp, out, p, sh);
 #if PB2_SHADE_PREFETCH >= 3
         // variant: the queue entry has arrived by now, so the prefetches do not wait for it
         if (valid_next) {
@@ -738,7 +748,35 @@ void render(Scene &s, const pb2_launch_params &lp) {
             ShadeOut so{ q_out, ctr_next + CTR_EXT, ctr + CTR_SHADOW, (float *)lp.albedo_buffer, (float *)lp.normal_buffer,
                          (float *)lp.test_buffer, last_batch ? (frames - 1) * n_pixels : ~0u };
             stage_begin(2);
-            if (sorted) {
+            // Kernels specialised by material type (k_shade<.., ONLY>: one BSDF compiled in instead of a seven-way switch).
+            // A scene with a single material type (unsorted mode) runs the kernel of that type: k_shade -11 % on the Cornell box.
+            // In the sorted mode one launch per material queue (PB2_SHADE_PER_TYPE=2) was measured as well and is 2 % SLOWER on
+            // the material grid than the single launch over all queues (eight short launches, each with its own tail), so
+            // that mode keeps the single launch (profiles/README.md).  Launches of the per-queue form follow each other on the
+            // stream in queue order, so the appended queues keep the order of the single-launch form.
+            uint32_t shade_launches = 1;
+            auto launch_only = [&](int type, const uint32_t *queue, const uint32_t *counts) {
+#define PB2_SHADE_CASE(T) \
+    case T: k_shade<6, SORTED_T, T><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, queue, counts, (uint32_t)ln.capacity, so); break;
+                if (sorted) {
+#define SORTED_T true
+                    switch (type) { PB2_SHADE_CASE(0) PB2_SHADE_CASE(1) PB2_SHADE_CASE(2) PB2_SHADE_CASE(3) PB2_SHADE_CASE(4) PB2_SHADE_CASE(5) PB2_SHADE_CASE(6) PB2_SHADE_CASE(7) default: break; }
+#undef SORTED_T
+                } else {
+#define SORTED_T false
+                    switch (type) { PB2_SHADE_CASE(1) PB2_SHADE_CASE(2) PB2_SHADE_CASE(3) PB2_SHADE_CASE(4) PB2_SHADE_CASE(5) PB2_SHADE_CASE(6) PB2_SHADE_CASE(7) default: break; }
+#undef SORTED_T
+                }
+#undef PB2_SHADE_CASE
+            };
+            const bool per_type = PB2_SHADE_PER_TYPE && s.shade_variant == 6 && (sorted ? (PB2_SHADE_PER_TYPE >= 2 && s.material_type_mask > 1u && !(s.material_type_mask & 1u)) : s.only_material_type >= 1);
+            if (per_type && sorted) {
+                shade_launches = 0;
+                for (int t = 0; t < (int)kNumTypes; ++t)
+                    if (t == 0 || (s.material_type_mask >> t) & 1u) launch_only(t, ln.q_mat.ptr, ctr + CTR_MAT0), ++shade_launches;
+            } else if (per_type) {
+                launch_only(s.only_material_type, q_in, ctr + CTR_EXT);
+            } else if (sorted) {
                 switch (s.shade_variant) {
                     case 4: k_shade<4, true><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
                     case 7: k_shade<7, true><<<grid_shade, kShadeThreads, 0, st>>>(sv, pa, fp, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, so); break;
@@ -755,7 +793,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
             }
             PB2_LAUNCH_CHECK();
             stage_end();
-            wf.launches += 2, ++wf.n_extend, ++wf.n_shade;
+            wf.launches += 1 + shade_launches, ++wf.n_extend, ++wf.n_shade;
             if (r + 1 < rounds) { // the last round cannot emit rays (depth >= max_depth)
                 stage_begin(3);
                 auto k = s.counting ? (coop ? k_shadow<true, true> : k_shadow<true, false>) : (coop ? k_shadow<false, true> : k_shadow<false, false>);
