@@ -47,19 +47,19 @@ struct AnyIO {
     }
 };
 
-template<bool COUNT, bool COOP>
+template<bool COUNT, bool COOP, bool TRIS = false>
 __global__ void __launch_bounds__(128, PB2_TRACE_MINB(COOP)) k_trace_closest(SceneView sv, ClosestIO io, uint32_t *__restrict__ work, unsigned long long *__restrict__ counters, int thr) {
     TraceCounters ctr{ 0, 0 };
-    trace_persistent<false, COUNT, COOP>(sv, io, work, &ctr, thr);
+    trace_persistent<false, COUNT, COOP, TRIS>(sv, io, work, &ctr, thr);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)ctr.nodes);
         atomicAdd(&counters[1], (unsigned long long)ctr.prims);
     }
 }
-template<bool COUNT, bool COOP>
+template<bool COUNT, bool COOP, bool TRIS = false>
 __global__ void __launch_bounds__(128, PB2_TRACE_MINB(COOP)) k_trace_any(SceneView sv, AnyIO io, uint32_t *__restrict__ work, unsigned long long *__restrict__ counters, int thr) {
     TraceCounters ctr{ 0, 0 };
-    trace_persistent<true, COUNT, COOP>(sv, io, work, &ctr, thr);
+    trace_persistent<true, COUNT, COOP, TRIS>(sv, io, work, &ctr, thr);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)ctr.nodes);
         atomicAdd(&counters[1], (unsigned long long)ctr.prims);
@@ -101,14 +101,16 @@ void trace_closest_dev(Scene &s, const float4 *rays, uint64_t n, float4 *hit_tuv
     if (!s.bvh_valid) throw std::runtime_error("pb2_trace_closest: call pb2_bvh_build first");
     if (!n) return;
     ClosestIO io{ rays, hit_tuvp, hit_inst, s.d_prims.ptr, (uint32_t)n };
-    if (s.use_coop_prims()) launch_trace(s, k_trace_closest<false, true>, k_trace_closest<true, true>, io, n);
-    else launch_trace(s, k_trace_closest<false, false>, k_trace_closest<true, false>, io, n);
+    const bool tris = s.build_stats.n_spheres == 0; // the plain kernels drop the sphere branch; the counting ones keep it (same counts)
+    if (s.use_coop_prims()) launch_trace(s, tris ? k_trace_closest<false, true, true> : k_trace_closest<false, true>, k_trace_closest<true, true>, io, n);
+    else launch_trace(s, tris ? k_trace_closest<false, false, true> : k_trace_closest<false, false>, k_trace_closest<true, false>, io, n);
 }
 void trace_any_dev(Scene &s, const float4 *rays, uint64_t n, uint32_t *occluded) {
     if (!s.bvh_valid) throw std::runtime_error("pb2_trace_any: call pb2_bvh_build first");
     if (!n) return;
     AnyIO io{ rays, occluded, (uint32_t)n };
-    if (s.use_coop_prims()) launch_trace(s, k_trace_any<false, true>, k_trace_any<true, true>, io, n);
-    else launch_trace(s, k_trace_any<false, false>, k_trace_any<true, false>, io, n);
+    const bool tris = s.build_stats.n_spheres == 0;
+    if (s.use_coop_prims()) launch_trace(s, tris ? k_trace_any<false, true, true> : k_trace_any<false, true>, k_trace_any<true, true>, io, n);
+    else launch_trace(s, tris ? k_trace_any<false, false, true> : k_trace_any<false, false>, k_trace_any<true, false>, io, n);
 }
 }// namespace pb2

@@ -49,11 +49,13 @@ PB2_D float3 ix_vector(float4 r0, float4 r1, float4 r2, float3 v) { return mk3(i
 
 // Tests one primitive record.  Returns true when it is hit closer than `hit.t`.
 // BRANCHLESS (triangles): the four early-outs folded into one predicate — see below; used where all 32 lanes test primitives.
-template<bool BRANCHLESS = false>
+// TRIS: the scene has no analytic spheres (pb2_build_stats::n_spheres == 0), the record kind is not looked at and the sphere
+// branch is compiled out: +1.7 % Msamples/s on the Cornell box, +3.9 % on the 30 M-triangle terrain (profiles/README.md).
+template<bool BRANCHLESS = false, bool TRIS = false>
 PB2_D bool intersect_prim(const SceneView &sv, uint32_t slot, float3 o, float3 d, float tmin, RayHit &hit) {
     const float4 *rec = reinterpret_cast<const float4 *>(sv.prims + slot);
     const float4 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
-    if (__float_as_uint(c.w) == 0u) {
+    if (TRIS || __float_as_uint(c.w) == 0u) {
         const float3 v0 = mk3(a), e1 = mk3(b), e2 = mk3(c);
         const float3 pvec = ix_cross(d, e2);
         const float det = ix_dot(e1, pvec);
@@ -249,7 +251,7 @@ struct CoopShared {                // per warp
 // (profiles/README.md): +7 % / +10 % Mrays/s for incoherent closest-hit / any-hit rays on the 30 M-triangle terrain, where
 // few lanes reach a leaf per step; -17 % on the 36-triangle Cornell box, where every lane does and the bookkeeping only
 // adds instructions.  The host picks per scene (Scene::coop_prims).
-template<bool ANY, bool COUNT, bool COOP, class IO>
+template<bool ANY, bool COUNT, bool COOP, bool TRIS, class IO>
 PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ work_counter, TraceCounters *ctr, int refill_threshold = PB2_REFILL_THRESHOLD) {
     constexpr uint32_t kFull = 0xffffffffu;
     __shared__ CoopShared s_coop[COOP ? kTraceWarps : 1];
@@ -292,7 +294,7 @@ PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ 
                 const uint32_t i = __ffs(r.T) - 1;
                 r.T &= r.T - 1;
                 if (COUNT) ++ctr->prims;
-                if (intersect_prim(sv, r.prim_base + i, r.o, r.d, r.tmin, r.hit)) {
+                if (intersect_prim<false, TRIS>(sv, r.prim_base + i, r.o, r.d, r.tmin, r.hit)) {
                     if (ANY) r.T = 0u, r.G.y = 0u, r.sp = 0;
                 }
             }
@@ -338,7 +340,7 @@ PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ 
                         const float4 ro = sm.o[own], rd = sm.d[own];
                         h.t = rd.w;
                         if (COUNT) ++ctr->prims;
-                        if (intersect_prim<true>(sv, sm.base[own] + (e & 31u), mk3(ro), mk3(rd), ro.w, h))
+                        if (intersect_prim<true, TRIS>(sv, sm.base[own] + (e & 31u), mk3(ro), mk3(rd), ro.w, h))
                             atomicMin(&sm.best[own], ((unsigned long long)__float_as_uint(h.t) << 32) | k); // t > 0: bit order = value order
                     }
                 }

@@ -228,24 +228,24 @@ struct ShadowIO {
     }
 };
 
-template<bool COUNT, bool COOP>
+template<bool COUNT, bool COOP, bool TRIS = false>
 __global__ void __launch_bounds__(128, PB2_TRACE_MINB(COOP)) k_extend(SceneView sv, PathArrays pa, const uint32_t *__restrict__ q_in, const uint32_t *__restrict__ n_in,
                                                 uint32_t *__restrict__ q_mat, uint32_t *__restrict__ mat_counts, uint32_t capacity, int sort,
                                                 uint32_t *__restrict__ work, unsigned long long *__restrict__ trav, int refill) {
     ExtendIO io{ sv, pa, q_in, q_mat, mat_counts, *n_in, capacity, sort };
     TraceCounters ctr{ 0, 0 };
-    trace_persistent<false, COUNT, COOP>(sv, io, work, &ctr, refill);
+    trace_persistent<false, COUNT, COOP, TRIS>(sv, io, work, &ctr, refill);
     if (COUNT) {
         atomicAdd(&trav[0], (unsigned long long)ctr.nodes);
         atomicAdd(&trav[1], (unsigned long long)ctr.prims);
     }
 }
-template<bool COUNT, bool COOP>
+template<bool COUNT, bool COOP, bool TRIS = false>
 __global__ void __launch_bounds__(128, PB2_TRACE_MINB(COOP)) k_shadow(SceneView sv, PathArrays pa, const uint32_t *__restrict__ n_in, uint32_t *__restrict__ work,
                                                 unsigned long long *__restrict__ trav, int refill) {
     ShadowIO io{ pa, *n_in, COUNT ? trav + 4 : nullptr };
     TraceCounters ctr{ 0, 0 };
-    trace_persistent<true, COUNT, COOP>(sv, io, work, &ctr, refill);
+    trace_persistent<true, COUNT, COOP, TRIS>(sv, io, work, &ctr, refill);
     if (COUNT) {
         atomicAdd(&trav[2], (unsigned long long)ctr.nodes);
         atomicAdd(&trav[3], (unsigned long long)ctr.prims);
@@ -673,6 +673,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const SceneView sv = s.view();
     const bool coop = s.use_coop_prims();
+    const bool tris = s.build_stats.n_spheres == 0; // no analytic spheres: the trace kernels without the sphere branch
     // material sorting pays when shading diverges: on by default only for scenes with more than one material type
     const bool sorted = s.sort_by_material == 1 || (s.sort_by_material < 0 && s.n_material_types > 1);
     wf.sorted = sorted, wf.lanes_used = n_lanes;
@@ -731,7 +732,8 @@ void render(Scene &s, const pb2_launch_params &lp) {
             uint32_t *q_in = ln.q_ext[r & 1].ptr, *q_out = ln.q_ext[(r + 1) & 1].ptr;
             stage_begin(1);
             {
-                auto k = s.counting ? (coop ? k_extend<true, true> : k_extend<true, false>) : (coop ? k_extend<false, true> : k_extend<false, false>);
+                auto k = s.counting ? (coop ? k_extend<true, true> : k_extend<true, false>)
+                                    : tris ? (coop ? k_extend<false, true, true> : k_extend<false, false, true>) : (coop ? k_extend<false, true> : k_extend<false, false>);
                 k<<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, sorted ? 1 : 0,
                                               ctr + CTR_WORK_EXT, s.counting ? wf.trav_counters.ptr : nullptr, s.refill_threshold);
             }
@@ -796,7 +798,8 @@ void render(Scene &s, const pb2_launch_params &lp) {
             wf.launches += 1 + shade_launches, ++wf.n_extend, ++wf.n_shade;
             if (r + 1 < rounds) { // the last round cannot emit rays (depth >= max_depth)
                 stage_begin(3);
-                auto k = s.counting ? (coop ? k_shadow<true, true> : k_shadow<true, false>) : (coop ? k_shadow<false, true> : k_shadow<false, false>);
+                auto k = s.counting ? (coop ? k_shadow<true, true> : k_shadow<true, false>)
+                                    : tris ? (coop ? k_shadow<false, true, true> : k_shadow<false, false, true>) : (coop ? k_shadow<false, true> : k_shadow<false, false>);
                 k<<<grid_trace, 128, 0, st>>>(sv, pa, ctr + CTR_SHADOW, ctr + CTR_WORK_SHADOW, s.counting ? wf.trav_counters.ptr : nullptr, s.refill_threshold);
                 PB2_LAUNCH_CHECK();
                 stage_end();
