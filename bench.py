@@ -360,7 +360,7 @@ def main():
         roofline["all_stage_frac"] = {k: v / peak for k, v in roofline["all_stage_gbs"].items()}
         if bvh_cached and dom in ("extend", "shadow"):
             roofline["note"] = (f"the {build.bvh_bytes}-byte BVH is cache resident, so this traversal kernel is bound by instruction issue, not by HBM "
-                                "(ncu: 77 % issue-slot utilisation, 18.5 of 32 lanes active, DRAM 14 % of peak; profiles/r1e_ncu.md); its HBM bytes are the "
+                                "(ncu: 76 % issue-slot utilisation, 19.4 of 32 lanes active, DRAM 14 % of peak; profiles/r1k_ncu.md); its HBM bytes are the "
                                 "ray and hit records only.  The HBM-bound kernel of the step is k_shade: see all_stage_frac")
 
     # ---- e2e: scene from HOST data every step, image back to the host -----------------------------------------------
