@@ -1,5 +1,6 @@
 #include "image.h"
 #include "image_ldr.h"
+#include "image_piz.h"
 #include "util.h"
 
 #include <zlib.h>
@@ -449,7 +450,8 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
     switch (compression) {
         case 0: case 1: case 2: lines_per_block = 1; break;
         case 3: lines_per_block = 16; break;
-        default: why = "compression " + std::to_string(compression) + " (only NONE, RLE, ZIPS, ZIP are read)"; return false;
+        case 4: lines_per_block = 32; break;
+        default: why = "compression " + std::to_string(compression) + " (only NONE, RLE, ZIPS, ZIP and PIZ are read)"; return false;
     }
     (void)line_order; // chunks carry their own y; the offset table is ignored and chunks are read in file order
     const size_t w = static_cast<size_t>(dw[2] - dw[0] + 1), h = static_cast<size_t>(dw[3] - dw[1] + 1);
@@ -479,6 +481,10 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
         } else if (compression == 1) {
             if (!ExrRleDecode(body, size, tmp, expect)) return false;
             ExrUnpredict(tmp, block);
+        } else if (compression == 4) {
+            std::vector<int> words;
+            for (auto &c : channels) words.push_back(static_cast<int>(c.bytes() / 2));
+            if (!piz::Decompress(body, size, w, lines, words, block) || block.size() != expect) return false;
         } else {
             tmp.resize(expect);
             uLongf len = static_cast<uLongf>(expect);
@@ -503,7 +509,7 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
                         v = static_cast<float>(u);
                     }
                     float *o = &img.rgba[((first + l) * w + x) * 4];
-                    if (slot == 4) o[0] = o[1] = o[2] = v;
+                    if (slot == 4) o[0] = o[1] = o[2] = o[3] = v; // LoadEXR copies a lone channel into all four, alpha included
                     else if (slot >= 0) o[slot] = v;
                 }
             }
