@@ -2,8 +2,8 @@
 // one tinyexr's LoadEXR (the reference's reader, framework/util/texture.cpp:131-149) handles.  Written from the published
 // description of the scheme (OpenEXR technical introduction; Imf PIZ: a 16-bit value range compaction through a bitmap-derived
 // lookup table, a two-dimensional Haar-like wavelet per channel plane, canonical Huffman coding with zero-run and repeat
-// symbols); tinyexr's code is not taken over.  tests/test_image_exr_piz.py holds the result to tinyexr compiled from the
-// reference tree (oracle/tinyexr_ref.cc), which also writes the test files.
+// symbols); tinyexr's code is not taken over.  tests/test_image_exr.py holds the result to tinyexr compiled from the
+// reference tree as a checker, which also writes the test files.
 #include "image_piz.h"
 
 #include <cstring>
