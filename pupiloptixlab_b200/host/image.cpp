@@ -655,8 +655,9 @@ bool LoadImage(std::string_view path, Image &out) noexcept {
             std::transform(ext.begin(), ext.end(), ext.begin(), [](unsigned char ch) { return static_cast<char>(std::tolower(ch)); });
             if (file.size() >= 3 && file[0] == 0xff && file[1] == 0xd8 && file[2] == 0xff) ok = ldr::LoadJpeg(file.data(), file.size(), px, why);
             else if (file.size() >= 2 && file[0] == 'B' && file[1] == 'M') ok = ldr::LoadBmp(file.data(), file.size(), px, why);
+            else if (file.size() >= 2 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) ok = ldr::LoadPnm(file.data(), file.size(), px, why);
             else if (ext == ".tga" && ldr::LooksLikeTga(file.data(), file.size())) ok = ldr::LoadTga(file.data(), file.size(), px, why); // no magic number
-            else why = "unsupported format (hdr, exr, png, jpeg, bmp, tga and pfm are read)";
+            else why = "unsupported format (hdr, exr, png, jpeg, bmp, tga, pgm / ppm and pfm are read)";
             if (ok) FromPixels8(px, out);
         }
         if (!ok || !out.Valid()) {

@@ -2,7 +2,7 @@
 // (framework/util/texture.cpp:13-174), which lean on stb_image / stb_image_write / tinyexr.  Those libraries are not
 // taken over; this is an own reader/writer for the formats the reference's scenes and output use:
 //   read : .hdr (Radiance RGBE, flat + new-style RLE), .exr (scan-line, NONE / RLE / ZIPS / ZIP / PIZ, HALF or FLOAT channels),
-//          .png (1-16 bit, grey / RGB / palette / alpha, Adam7), .jpg (baseline + progressive), .bmp, .tga (image_ldr.cpp), .pfm
+//          .png (1-16 bit, grey / RGB / palette / alpha, Adam7), .jpg (baseline + progressive), .bmp, .tga, .pgm / .ppm (image_ldr.cpp), .pfm
 //   write: .hdr (RGBE), .exr (3 FLOAT channels B, G, R, ZIP), .pfm
 // Conventions kept from the reference: texels are RGBA float, row 0 = first row of the file (no flip on load); 8-bit
 // sources are linearised with pow(x / 255, 2.2) and alpha / 255 (texture.cpp:104-115); HDR sources are taken as they

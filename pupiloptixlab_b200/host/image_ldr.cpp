@@ -661,6 +661,43 @@ bool LoadBmp(const uint8_t *file, size_t n, Pixels8 &out, std::string &why) {
     return true;
 }
 
+bool LoadPnm(const uint8_t *file, size_t n, Pixels8 &out, std::string &why) {
+    auto fail = [&](const char *m) {
+        why = std::string("pnm: ") + m;
+        return false;
+    };
+    if (n < 3 || file[0] != 'P' || (file[1] != '5' && file[1] != '6')) return fail("only binary P5 / P6 files are read");
+    size_t pos = 2;
+    auto number = [&](int &v) -> bool { // white space and # comments, then decimal digits
+        for (;;) {
+            while (pos < n && (file[pos] == ' ' || file[pos] == '\t' || file[pos] == '\r' || file[pos] == '\n' || file[pos] == '\f' || file[pos] == '\v')) ++pos;
+            if (pos < n && file[pos] == '#') {
+                while (pos < n && file[pos] != '\n' && file[pos] != '\r') ++pos;
+            } else break;
+        }
+        if (pos >= n || file[pos] < '0' || file[pos] > '9') return false;
+        long long x = 0;
+        while (pos < n && file[pos] >= '0' && file[pos] <= '9' && x < (1ll << 31)) x = x * 10 + (file[pos++] - '0');
+        v = static_cast<int>(x < (1ll << 31) ? x : -1);
+        return v >= 0;
+    };
+    int w = 0, h = 0, maxval = 0;
+    if (!number(w) || !number(h) || !number(maxval)) return fail("bad header");
+    if (w <= 0 || h <= 0 || maxval <= 0 || maxval > 65535 || static_cast<uint64_t>(w) * h > (1ull << 28)) return fail("bad header");
+    if (pos >= n) return fail("truncated pixel data");
+    ++pos; // the single white-space byte after maxval
+    const int channels = file[1] == '6' ? 3 : 1, bytes = maxval > 255 ? 2 : 1;
+    const size_t count = static_cast<size_t>(w) * h * channels;
+    if ((n - pos) / bytes < count) return fail("truncated pixel data");
+    out.w = w, out.h = h, out.channels = channels;
+    out.data.resize(count);
+    // 16-bit samples are stored big endian.  stb_image (the reference's reader) loads them as host words without swapping, so on
+    // the little-endian hosts it runs on its 8-bit API hands back the SECOND byte of each sample; the same byte is taken here so
+    // that such a texture yields the texels the reference would see
+    for (size_t i = 0; i < count; ++i) out.data[i] = file[pos + i * bytes + (bytes - 1)];
+    return true;
+}
+
 bool LooksLikeTga(const uint8_t *f, size_t n) {
     if (n < 18) return false;
     const int cmap = f[1], type = f[2], bpp = f[16];

@@ -21,5 +21,7 @@ bool LoadJpeg(const uint8_t *file, size_t n, Pixels8 &out, std::string &why);
 bool LoadBmp(const uint8_t *file, size_t n, Pixels8 &out, std::string &why);
 // Truevision TGA: colour-mapped, true-colour and grey images, raw or run-length encoded, 8 / 15 / 16 / 24 / 32 bit
 bool LoadTga(const uint8_t *file, size_t n, Pixels8 &out, std::string &why);
+// binary portable pixmaps: P5 (grey) and P6 (RGB), maxval < 65536 (16-bit samples reduced to the byte stb_image's 8-bit API keeps)
+bool LoadPnm(const uint8_t *file, size_t n, Pixels8 &out, std::string &why);
 bool LooksLikeTga(const uint8_t *file, size_t n); // TGA has no magic number: header plausibility
 }// namespace Pupil::util::ldr

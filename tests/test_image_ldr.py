@@ -407,3 +407,21 @@ def test_corrupted_files_are_decoded_or_refused_never_worse(tmp_path):
                     pass
     finally:
         pupil.lib().pupil_set_log_level(1)
+
+
+# ---- PGM / PPM ------------------------------------------------------------------------------------------------------
+def test_binary_pnm(tmp_path):
+    rng = np.random.default_rng(14)
+    rgb = rng.integers(0, 256, (7, 9, 3), dtype=np.uint8)
+    got = check(tmp_path / "a.ppm", b"P6\n# a comment\n9 7\n255\n" + rgb.tobytes())
+    assert np.allclose(got, expected_rgba(rgb), rtol=3e-6, atol=1e-7)
+    grey = rng.integers(0, 256, (5, 4, 1), dtype=np.uint8)
+    got = check(tmp_path / "g.pgm", b"P5 4 5 255\n" + grey.tobytes())
+    assert np.allclose(got, expected_rgba(grey), rtol=3e-6, atol=1e-7)
+    deep = rng.integers(0, 65536, (3, 5, 3), dtype=np.uint16)
+    got = check(tmp_path / "d.ppm", b"P6\n5 3\n65535\n" + deep.astype(">u2").tobytes(), pil=False)  # Pillow rescales 16-bit PPM differently
+    assert np.allclose(got, expected_rgba((deep & 255).astype(np.uint8)), rtol=3e-6, atol=1e-7)  # the byte stb_image keeps on little-endian hosts
+    for name, data in {"ascii.ppm": b"P3\n1 1\n255\n1 2 3\n", "cut.ppm": b"P6\n9 7\n255\n" + rgb.tobytes()[:-1], "zero.pgm": b"P5 0 5 255\n"}.items():
+        (tmp_path / name).write_bytes(data)
+        with pytest.raises(pupil.PupilError):
+            pupil.image_load(tmp_path / name)
