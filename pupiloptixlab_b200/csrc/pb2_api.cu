@@ -108,7 +108,21 @@ void Scene::upload_tables() {
     n_material_types = __builtin_popcount(seen);
     only_material_type = n_material_types == 1 ? __builtin_ctz(seen) : -1;
     material_type_mask = seen;
-    d_inst.upload(h_inst.data(), h_inst.size(), stream);
+    // Texture coordinates are fetched and interpolated per shaded vertex only where they can change the result: an instance
+    // whose material textures (and, for an emitter, radiance textures) are all constant colours is uploaded without
+    // PB2_IF_HAS_UV (the host copy keeps the flag).
+    std::vector<DevInstance> dev_inst = h_inst;
+    auto constant = [](const DevTexture &t) { return __builtin_bit_cast(int32_t, t.hdr.x) == PB2_TEX_RGB; };
+    for (size_t i = 0; i < dev_inst.size(); ++i) {
+        DevInstance &in = dev_inst[i];
+        if (!(in.flags & PB2_IF_HAS_UV) || i >= h_mat.size()) continue;
+        bool uv_matters = false;
+        for (const DevTexture &t : h_mat[i].tex) uv_matters |= !constant(t);
+        if (in.emitter_offset >= 0)
+            for (uint64_t e = (uint64_t)in.emitter_offset, end = e + in.n_tris; e < end; ++e) uv_matters |= e >= h_areas.size() || !constant(h_areas[e].radiance);
+        if (!uv_matters) in.flags &= ~PB2_IF_HAS_UV;
+    }
+    d_inst.upload(dev_inst.data(), dev_inst.size(), stream);
     d_mat.upload(h_mat.data(), h_mat.size(), stream);
     d_areas.upload(h_areas.data(), h_areas.size(), stream);
     std::vector<float> cdf = area_select_cdf(h_areas.data(), h_areas.size());
