@@ -407,10 +407,13 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
     Reader r(file.data(), file.size());
     if (r.le<uint32_t>() != 20000630u) return false;
     const uint32_t version = r.le<uint32_t>();
-    if ((version & 0xffu) != 2 || (version & 0x1a00u)) { // tiles, deep data or multi-part
-        why = "only single-part scan-line EXR files are read";
+    if ((version & 0xffu) != 2 || (version & 0x1800u)) { // deep data or multi-part
+        why = "only single-part flat EXR files are read";
         return false;
     }
+    const bool tiled = (version & 0x200u) != 0;
+    uint32_t tile_w = 0, tile_h = 0;
+    int tile_mode = -1;
     std::vector<ExrChannel> channels;
     int compression = -1, line_order = 0;
     int dw[4] = { 0, 0, -1, -1 };
@@ -443,6 +446,9 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
             std::memcpy(dw, body, 16);
         } else if (name == "lineOrder" && size >= 1) {
             line_order = body[0];
+        } else if (name == "tiles" && size >= 9) {
+            std::memcpy(&tile_w, body, 4), std::memcpy(&tile_h, body + 4, 4);
+            tile_mode = body[8];
         }
     }
     if (channels.empty() || dw[2] < dw[0] || dw[3] < dw[1]) return false;
@@ -455,10 +461,17 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
     }
     (void)line_order; // chunks carry their own y; the offset table is ignored and chunks are read in file order
     const size_t w = static_cast<size_t>(dw[2] - dw[0] + 1), h = static_cast<size_t>(dw[3] - dw[1] + 1);
-    const size_t n_blocks = (h + lines_per_block - 1) / lines_per_block;
+    if (tiled && (tile_mode < 0 || (tile_mode & 0xf) != 0 || !tile_w || !tile_h)) {
+        why = "only single-level (ONE_LEVEL) tiled files are read";
+        return false;
+    }
+    const size_t tiles_x = tiled ? (w + tile_w - 1) / tile_w : 0, tiles_y = tiled ? (h + tile_h - 1) / tile_h : 0;
+    const size_t n_blocks = tiled ? tiles_x * tiles_y : (h + lines_per_block - 1) / lines_per_block;
+    if (n_blocks > file.size() / 8) return false;
     r.take(n_blocks * 8);
-    size_t line_bytes = 0;
-    for (auto &c : channels) line_bytes += c.bytes() * w;
+    size_t pixel_bytes = 0;
+    for (auto &c : channels) pixel_bytes += c.bytes();
+    const size_t line_bytes = pixel_bytes * w;
     // channel -> RGBA slot; a single channel (luminance) is replicated like tinyexr's LoadEXR does
     auto slot_of = [&](const std::string &n) { return n == "R" ? 0 : n == "G" ? 1 : n == "B" ? 2 : n == "A" ? 3 : -1; };
     // the offset table must fit, and zlib / RLE expand by at most ~1032 : 1: a data window the file's bytes cannot fill is corrupt
@@ -468,13 +481,9 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
     img.rgba.assign(w * h * 4, 0.f);
     for (size_t i = 0; i < w * h; ++i) img.rgba[i * 4 + 3] = 1.f;
     std::vector<uint8_t> tmp, block;
-    for (size_t b = 0; b < n_blocks; ++b) {
-        const int y0 = r.le<int32_t>();
-        const uint32_t size = r.le<uint32_t>();
-        const uint8_t *body = r.take(size);
-        if (!r.ok || !body || y0 < dw[1] || y0 > dw[3]) return false;
-        const size_t first = static_cast<size_t>(y0 - dw[1]), lines = std::min<size_t>(lines_per_block, h - first);
-        const size_t expect = lines * line_bytes;
+    // one chunk (a block of scan lines, or a tile): cw x lines pixels whose top-left corner is (x0, first) of the picture
+    auto chunk = [&](const uint8_t *body, uint32_t size, size_t x0, size_t first, size_t cw, size_t lines) -> bool {
+        const size_t expect = lines * pixel_bytes * cw;
         if (compression == 0 || size == expect) { // stored raw (also what writers do when compression does not pay)
             if (size != expect) return false;
             block.assign(body, body + size);
@@ -484,7 +493,7 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
         } else if (compression == 4) {
             std::vector<int> words;
             for (auto &c : channels) words.push_back(static_cast<int>(c.bytes() / 2));
-            if (!piz::Decompress(body, size, w, lines, words, block) || block.size() != expect) return false;
+            if (!piz::Decompress(body, size, cw, lines, words, block) || block.size() != expect) return false;
         } else {
             tmp.resize(expect);
             uLongf len = static_cast<uLongf>(expect);
@@ -495,7 +504,7 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
         for (size_t l = 0; l < lines; ++l)
             for (auto &c : channels) {
                 const int slot = channels.size() == 1 ? 4 : slot_of(c.name);
-                for (size_t x = 0; x < w; ++x, p += c.bytes()) {
+                for (size_t x = 0; x < cw; ++x, p += c.bytes()) {
                     float v;
                     if (c.type == 1) {
                         uint16_t hv;
@@ -508,11 +517,29 @@ bool LoadExr(const std::vector<uint8_t> &file, Image &img, std::string &why) {
                         std::memcpy(&u, p, 4);
                         v = static_cast<float>(u);
                     }
-                    float *o = &img.rgba[((first + l) * w + x) * 4];
+                    float *o = &img.rgba[((first + l) * w + x0 + x) * 4];
                     if (slot == 4) o[0] = o[1] = o[2] = o[3] = v; // LoadEXR copies a lone channel into all four, alpha included
                     else if (slot >= 0) o[slot] = v;
                 }
             }
+        return true;
+    };
+    for (size_t b = 0; b < n_blocks; ++b) {
+        if (tiled) { // tile coordinates, level (0, 0), size, data
+            const int tx = r.le<int32_t>(), ty = r.le<int32_t>(), lx = r.le<int32_t>(), ly = r.le<int32_t>();
+            const uint32_t size = r.le<uint32_t>();
+            const uint8_t *body = r.take(size);
+            if (!r.ok || !body || tx < 0 || ty < 0 || static_cast<size_t>(tx) >= tiles_x || static_cast<size_t>(ty) >= tiles_y || lx != 0 || ly != 0) return false;
+            const size_t x0 = static_cast<size_t>(tx) * tile_w, y0 = static_cast<size_t>(ty) * tile_h;
+            if (!chunk(body, size, x0, y0, std::min<size_t>(tile_w, w - x0), std::min<size_t>(tile_h, h - y0))) return false;
+        } else {
+            const int y0 = r.le<int32_t>();
+            const uint32_t size = r.le<uint32_t>();
+            const uint8_t *body = r.take(size);
+            if (!r.ok || !body || y0 < dw[1] || y0 > dw[3]) return false;
+            const size_t first = static_cast<size_t>(y0 - dw[1]);
+            if (!chunk(body, size, 0, first, w, std::min<size_t>(lines_per_block, h - first))) return false;
+        }
     }
     return true;
 }

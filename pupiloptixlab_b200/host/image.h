@@ -1,7 +1,7 @@
 // Image files for bitmap textures, environment maps and saved frames — the role of util::BitmapTexture::Load / Save
 // (framework/util/texture.cpp:13-174), which lean on stb_image / stb_image_write / tinyexr.  Those libraries are not
 // taken over; this is an own reader/writer for the formats the reference's scenes and output use:
-//   read : .hdr (Radiance RGBE, flat + new-style RLE), .exr (scan-line, NONE / RLE / ZIPS / ZIP / PIZ, HALF or FLOAT channels),
+//   read : .hdr (Radiance RGBE, flat + new-style RLE), .exr (scan-line or single-level tiled, NONE / RLE / ZIPS / ZIP / PIZ, HALF or FLOAT channels),
 //          .png (1-16 bit, grey / RGB / palette / alpha, Adam7), .jpg (baseline + progressive), .bmp, .tga, .pgm / .ppm (image_ldr.cpp), .pfm
 //   write: .hdr (RGBE), .exr (3 FLOAT channels B, G, R, ZIP), .pfm
 // Conventions kept from the reference: texels are RGBA float, row 0 = first row of the file (no flip on load); 8-bit

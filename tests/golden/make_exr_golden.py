@@ -43,6 +43,13 @@ def main():
         assert T.exr_ref_save(str(path).encode(), img.ctypes.data, w, h, ch, 4, half) == 0
         out[name] = ref_load(path)
         print(name, path.stat().st_size, "bytes")
+    # a single-level tiled file (16 x 8 tiles, PIZ, ragged right and bottom edges)
+    T.exr_ref_save_tiled.argtypes = [C.c_char_p, C.c_void_p] + [C.c_int] * 7
+    img = picture(21, 43, 3, 4)
+    path = HERE / "exr" / "tiled_piz_rgb_half.exr"
+    assert T.exr_ref_save_tiled(str(path).encode(), img.ctypes.data, 43, 21, 3, 4, 1, 16, 8) == 0
+    out["tiled_piz_rgb_half"] = ref_load(path)
+    print("tiled_piz_rgb_half", path.stat().st_size, "bytes")
     np.savez_compressed(HERE / "exr_reference.npz", **out)
 
 

@@ -22,7 +22,7 @@ GOLD = ROOT / "tests" / "golden"
 
 def test_piz_fixtures_match_the_reference_reader():
     want = np.load(GOLD / "exr_reference.npz")
-    assert sorted(want.files) == ["piz_rgb_half", "piz_rgba_float", "piz_y_half"]
+    assert sorted(want.files) == ["piz_rgb_half", "piz_rgba_float", "piz_y_half", "tiled_piz_rgb_half"]
     for name in want.files:
         got = pupil.image_load(GOLD / "exr" / f"{name}.exr")
         assert got.shape == want[name].shape and np.array_equal(got.view(np.uint32), want[name].view(np.uint32)), name
@@ -90,6 +90,30 @@ def test_reader_equals_tinyexr(tmp_path, compression, half):
         want, got = _ref_load(path), pupil.image_load(path)
         assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (ch, h, w, kind)
     assert compression != 4 or written >= 5
+
+
+@needs_tinyexr
+@pytest.mark.parametrize("compression", [0, 1, 3, 4], ids=["none", "rle", "zip", "piz"])
+def test_tiled_files_equal_tinyexr(tmp_path, compression):
+    """single-level tiled files (the other layout LoadEXR reads): tiles that do not divide the picture, tiles larger than it"""
+    child = ("import ctypes as C, numpy as np, sys; a = np.load(sys.argv[2]); T = C.CDLL(sys.argv[1]); "
+             "T.exr_ref_save_tiled.argtypes = [C.c_char_p, C.c_void_p] + [C.c_int] * 7; "
+             "sys.exit(T.exr_ref_save_tiled(sys.argv[3].encode(), a.ctypes.data, a.shape[1], a.shape[0], a.shape[2], int(sys.argv[4]), int(sys.argv[5]), "
+             "int(sys.argv[6]), int(sys.argv[7])))")
+    written = 0
+    for ch, (h, w), (tw, th), half in ((3, (40, 50), (16, 16), 1), (4, (33, 70), (32, 8), 0), (1, (20, 20), (8, 8), 1), (3, (64, 64), (64, 64), 0), (3, (17, 5), (4, 16), 1)):
+        y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+        img = np.ascontiguousarray(np.stack([np.round((np.sin(x / 7 + y / 3) + 1) * 16) / 16, x / w, y / h, 0 * x + 0.5], -1)[..., :ch], np.float32)
+        np.save(tmp_path / "img.npy", img)
+        path = tmp_path / f"t{ch}_{h}x{w}.exr"
+        r = subprocess.run([sys.executable, "-c", child, str(ROOT / "oracle" / "_ref" / "libtinyexr_ref.so"), str(tmp_path / "img.npy"), str(path), str(compression),
+                            str(half), str(tw), str(th)], capture_output=True)
+        if r.returncode != 0:
+            continue  # tinyexr's writer refuses tiles larger than the picture and is fragile on incompressible data
+        written += 1
+        want, got = _ref_load(path), pupil.image_load(path)
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (ch, h, w, tw, th)
+    assert written >= 3
 
 
 @needs_tinyexr
