@@ -181,7 +181,7 @@ struct JpegDecoder {
         if (p[0] != 8) return Fail("only 8-bit samples are read");
         height = Be16(p + 1), width = Be16(p + 3), n_comp = p[5];
         if (!width || !height) return Fail("zero size (DNL-defined heights are not read)");
-        if (n_comp != 1 && n_comp != 3) return Fail("only 1- and 3-component pictures are read");
+        if (n_comp != 1 && n_comp != 3 && n_comp != 4) return Fail("only 1-, 3- and 4-component pictures are read");
         if (len < 6 + 3 * n_comp) return Fail("short SOF");
         if (static_cast<uint64_t>(width) * height > (1ull << 28)) return Fail("picture too large");
         progressive = marker == 0xc2;
@@ -449,8 +449,10 @@ struct JpegDecoder {
     bool Output(Pixels8 &out) {
         const bool rgb_ids = n_comp == 3 && comp[0].id == 'R' && comp[1].id == 'G' && comp[2].id == 'B';
         const bool direct_rgb = n_comp == 3 && (rgb_ids || (adobe_transform == 0 && !jfif));
-        out.w = width, out.h = height, out.channels = n_comp;
-        out.data.assign(static_cast<size_t>(width) * height * n_comp, 0);
+        // four components are print colours (Adobe CMYK, or YCCK when the APP14 transform flag is 2) and come out as RGB
+        const int n_out = n_comp == 4 ? 3 : n_comp;
+        out.w = width, out.h = height, out.channels = n_out;
+        out.data.assign(static_cast<size_t>(width) * height * n_out, 0);
         struct Walk {
             int hs, vs, step, row, line0, line1;
         } walk[4];
@@ -484,8 +486,17 @@ struct JpegDecoder {
                     if (++k.row < c.px_h) ++k.line1;
                 }
             }
-            uint8_t *o = out.data.data() + static_cast<size_t>(y) * width * n_comp;
+            uint8_t *o = out.data.data() + static_cast<size_t>(y) * width * n_out;
+            auto mul255 = [](int a, int b) { // a * b / 255, rounded (the 8 x 8 bit product rule stb_image uses for CMYK)
+                const int t = a * b + 128;
+                return static_cast<uint8_t>((t + (t >> 8)) >> 8);
+            };
             if (n_comp == 1) std::memcpy(o, src[0], static_cast<size_t>(width));
+            else if (n_comp == 4 && adobe_transform == 0)
+                for (int x = 0; x < width; ++x) {
+                    const int k = src[3][x];
+                    o[3 * x] = mul255(src[0][x], k), o[3 * x + 1] = mul255(src[1][x], k), o[3 * x + 2] = mul255(src[2][x], k);
+                }
             else if (direct_rgb)
                 for (int x = 0; x < width; ++x) o[3 * x] = src[0][x], o[3 * x + 1] = src[1][x], o[3 * x + 2] = src[2][x];
             else { // YCbCr -> RGB in 20-bit fixed point (coefficients rounded to 12 bits; the Cb term of green drops its low 16 bits)
@@ -496,6 +507,10 @@ struct JpegDecoder {
                     const int g = yy + cr * kCrG + static_cast<int>(static_cast<uint32_t>(cb * kCbG) & 0xffff0000u);
                     const int b = yy + cb * kCbB;
                     o[3 * x] = Clamp8(r >> 20), o[3 * x + 1] = Clamp8(g >> 20), o[3 * x + 2] = Clamp8(b >> 20);
+                    if (n_comp == 4 && adobe_transform == 2) { // YCCK: the three colours are stored inverted, then scaled by K
+                        const int k = src[3][x];
+                        o[3 * x] = mul255(255 - o[3 * x], k), o[3 * x + 1] = mul255(255 - o[3 * x + 1], k), o[3 * x + 2] = mul255(255 - o[3 * x + 2], k);
+                    }
                 }
             }
         }

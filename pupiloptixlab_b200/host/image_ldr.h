@@ -15,7 +15,7 @@ struct Pixels8 {
     int w = 0, h = 0, channels = 0; // 1 grey, 2 grey + alpha, 3 RGB, 4 RGBA; row 0 = top of the picture
     std::vector<uint8_t> data;      // interleaved
 };
-// baseline, extended-sequential and progressive Huffman JPEG, 8 bit, 1 or 3 components
+// baseline, extended-sequential and progressive Huffman JPEG, 8 bit, 1, 3 or 4 (CMYK / YCCK, returned as RGB) components
 bool LoadJpeg(const uint8_t *file, size_t n, Pixels8 &out, std::string &why);
 // Windows bitmaps: 1 / 4 / 8 bit palettised, 16 / 24 / 32 bit direct colour (BI_RGB, BI_BITFIELDS), either row order
 bool LoadBmp(const uint8_t *file, size_t n, Pixels8 &out, std::string &why);

@@ -425,3 +425,20 @@ def test_binary_pnm(tmp_path):
         (tmp_path / name).write_bytes(data)
         with pytest.raises(pupil.PupilError):
             pupil.image_load(tmp_path / name)
+
+
+def test_jpeg_four_components(tmp_path):
+    """Adobe CMYK (APP14 transform 0, what Pillow writes), and the same file relabelled YCCK (2) and "YCbCr + K" (1): stb_image returns
+    RGB for all three, and so does the host library — compared with stb only (Pillow keeps CMYK)"""
+    if STB is None:
+        pytest.skip("needs the reference's stb_image as checker")
+    cmyk = PIL.fromarray(_picture(40, 56, 3)).convert("CMYK")
+    for kw in (dict(quality=90), dict(quality=85, progressive=True), dict(quality=90, subsampling=0)):
+        b = io.BytesIO()
+        cmyk.save(b, "JPEG", **kw)
+        data = bytearray(b.getvalue())
+        flag = data.index(b"Adobe") + 11
+        for transform in (0, 1, 2):
+            data[flag] = transform
+            got = check(tmp_path / f"c{transform}.jpg", bytes(data), pil=False)
+            assert got.shape == (40, 56, 4) and np.all(got[..., 3] == 1.0)
