@@ -97,7 +97,8 @@ typedef struct pb2_hit {
  * in the scene handle).  Buffers are DEVICE pointers, row-major, pixel_index = y*width + x, row 0 = bottom. */
 typedef struct pb2_launch_params {
     uint32_t max_depth;
-    uint32_t accumulate;   /* 0: overwrite, 1: running mean (main.cu:190-194), 2: plain sum (multi-GPU shards) */
+    uint32_t accumulate;   /* 0: overwrite, 1: running mean (main.cu:190-194), 2: plain sums, w = frames summed (multi-GPU
+                              shards); in modes 1 and 2 sample_cnt = 0 starts over without reading the buffer */
     uint32_t width, height;
     uint32_t random_seed;  /* seed of the first frame */
     uint32_t seed_stride;  /* frame i uses random_seed + i*seed_stride (0 is read as 1) */
@@ -214,14 +215,35 @@ int pb2_render_stats_get(pb2_scene *scene, pb2_render_stats *stats); /* synchron
  * by scene size), l2_persist_mb / l2_window_mb (persisting-L2 access-policy window over the top levels of the node array;
  * 0 = off, the default).  Unknown names fail with PB2_ERR_ARG. */
 int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value);
-/* multi-GPU shards render with accumulate = 2 (sum); after the cross-GPU reduction the root calls this:
- * frame[i] = (sum[i].xyz / total_spp, 1).   */
+/* frame[i] = (sum[i].xyz / total_spp, 1) on the scene's stream: the last step of a sharded render whose sums were combined
+ * by the caller's own collective (pb2_comm_reduce_frames below does both).   */
 int pb2_finalize_sum(pb2_scene *scene, const void *sum_buffer, void *frame_buffer, uint64_t n_pixels, uint32_t total_spp);
 
-/* per-function device known-answer hooks (tests only): run the device restatement of one function of
- * framework/render/material, framework/render/emitter, framework/optix/util.h, framework/cuda/random.h over
- * n inputs.  `what` selects the function; layouts are documented next to pb2_kat in csrc/kat.cu. */
-int pb2_kat(const char *what, const void *in0, const void *in1, const void *in2, uint64_t n, void *out);
+/* ---- multi-GPU: one process per GPU, sample-index shards, NCCL over NVLink --------------------------
+ * The reference renders on one GPU (example/path_tracer/pt_pass.cpp:39-57); these entry points have no counterpart there.
+ * Every rank loads the same scene, renders the seeds pb2_shard_plan gives it with accumulate = 2 and then calls
+ * pb2_comm_reduce_frames, which adds the ranks' sum buffers and writes frame = sum / total_spp.  NCCL is loaded at run time
+ * (libnccl.so.2); a communicator of one rank needs none. */
+typedef struct pb2_comm pb2_comm;
+#define PB2_COMM_ID_BYTES 128
+#define PB2_REDUCE_ROOT 0 /* ncclReduce to `root`, which finalizes: only the root's frame buffer is written */
+#define PB2_REDUCE_ALL 1  /* ncclReduceScatter, each rank finalizes 1/N of the pixels, ncclAllGather: every rank gets the frame
+                             (falls back to PB2_REDUCE_ROOT when the ranks do not divide the pixel count) */
+int pb2_comm_unique_id(uint8_t id[PB2_COMM_ID_BYTES]); /* rank 0; the caller hands the bytes to the other ranks */
+/* collective over the ranks; binds the communicator to the CURRENT device (pb2_init) */
+int pb2_comm_create(pb2_comm **comm, int n_ranks, int rank, const uint8_t id[PB2_COMM_ID_BYTES]);
+int pb2_comm_destroy(pb2_comm *comm);
+/* Asynchronous: ordered after everything queued on the scene's stream, runs on the communicator's stream.  The scene's next
+ * pb2_render overlaps it up to its first accumulate kernel (the only writer of sum_buffer), which waits; read the frame
+ * after pb2_comm_synchronize.  frame_buffer may be NULL on non-root ranks in PB2_REDUCE_ROOT mode. */
+int pb2_comm_reduce_frames(pb2_comm *comm, pb2_scene *scene, const void *sum_buffer, void *frame_buffer, uint64_t n_pixels, uint32_t total_spp,
+                           int mode, int root);
+int pb2_comm_synchronize(pb2_comm *comm);
+int pb2_comm_nccl_version(int *version);
+/* the seeds of `rank` in progressive step `step`: first_seed + k * seed_stride, k < spp_rank.  strong = 0: every rank renders
+ * `spp` frames (the step holds spp * n_ranks); strong = 1: the step's `spp` frames are split over the ranks. */
+int pb2_shard_plan(int rank, int n_ranks, uint32_t step, uint32_t spp, int strong, uint32_t *first_seed, uint32_t *seed_stride,
+                   uint32_t *spp_rank, uint32_t *spp_total);
 
 #ifdef __cplusplus
 }

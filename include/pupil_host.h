@@ -41,6 +41,16 @@ int pupil_clear_shapes(void);
  * (pt_pass.cpp:256-268); frames_per_run = frames executed per PTPass::OnRun; first_seed / seed_stride = the
  * random_seed sequence (reference: 0, 1); sum_mode != 0 accumulates plain sums (multi-GPU shards). */
 int pupil_pass_config(int max_depth, int accumulate, uint32_t frames_per_run, uint32_t first_seed, uint32_t seed_stride, int sum_mode);
+/* Multi-GPU, one process per GPU (the reference is single-GPU).  rank 0 obtains the id and hands it to the other
+ * ranks out of band; pupil_set_shard is collective (ncclCommInitRank) and binds this process, on the device of pupil_init, as
+ * `rank` of `world`.  From then on one pass run renders this rank's seeds of the step (strong != 0: frames_per_run is the
+ * step's TOTAL sample count, split over the ranks; else every rank renders frames_per_run), queues the NCCL reduction
+ * (reduce_mode PB2_REDUCE_ROOT / PB2_REDUCE_ALL) and returns without waiting: "final result" holds sum / total spp after
+ * pupil_synchronize (buffer downloads synchronise on their own).  world <= 0 switches sharding off. */
+int pupil_comm_unique_id(uint8_t id[128]);
+int pupil_set_shard(int rank, int world, const uint8_t *id, int strong, int reduce_mode);
+int pupil_set_shard_plan(int strong); /* switch between the weak and the strong plan, keeping the communicator */
+int pupil_synchronize(void);
 /* System::Run() for n_pass_runs iterations of the pass list (headless: returns instead of looping forever) */
 int pupil_run(uint64_t n_pass_runs);
 /* frames (samples per pixel) accumulated so far and the next random_seed */
@@ -78,6 +88,9 @@ int pupil_get_env_tables(uint32_t *map_w, uint32_t *map_h, float *row_cdf, float
  * object-to-world matrix.  Its area emitters are rebuilt (EmitterHelper::ResetAreaEmitter), the acceleration structure is
  * rebuilt on the next run and the pass restarts its accumulation, as after IAS::Update in the reference. */
 int pupil_set_instance_transform(uint32_t index, const float xform[16]);
+/* World::RemoveRenderObject (framework/world/world.cpp) on the index-th render object: the object, its entries of the emitter
+ * table and its share of the selection probabilities go; later objects keep their order (their emitter offsets move down). */
+int pupil_remove_instance(uint32_t index);
 int pupil_num_area_emitters(void);
 int pupil_get_emitters(pb2_emitter *areas, pb2_emitter *env, int32_t *has_env);
 /* World::GetSceneHandle(): the pb2 scene (BVH built, camera and emitters uploaded) for pb2_trace_* etc. */

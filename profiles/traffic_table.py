@@ -3,12 +3,15 @@
 gpu__time_duration.sum over the trace / shade kernels of one bench.py run) -> profiles/roofline_traffic.json, the
 measured DRAM bytes per launch that bench.py reports as roofline.traffic."""
 import collections
+import sys
 import csv
 import json
 import re
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tools"))
+from source_hash import kernel_source_sha  # noqa: E402
 out = {}
 for w in ["cornell", "material_grid", "terrain"]:
     lines = [l for l in open(ROOT / "gpurun_out" / f"traffic_{w}.csv") if not l.startswith("==")]
@@ -28,6 +31,6 @@ for w in ["cornell", "material_grid", "terrain"]:
             print(w, k, len(sel), "launches/step,", round(per[k.replace("k_", "")] / 1e6, 1), "MB/launch,",
                   round(1e3 * sum(l["gpu__time_duration.sum"] for l in sel) / len(sel), 3), "ms/launch under ncu")
     out[w] = per
-json.dump({"_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the launches of one timed bench.py step "
-                       "(tools/run_traffic.sh, profiles/traffic_table.py); bench.py copies the dominant kernel's figure into roofline.traffic", **out},
+json.dump({"kernel_source_sha": kernel_source_sha(), "_comment": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the launches of one timed bench.py step "
+                       "(tools/run_traffic.sh, profiles/traffic_table.py); bench.py copies the dominant kernel's figure into roofline.traffic while kernel_source_sha (tools/source_hash.py) still matches the sources it runs", **out},
           open(ROOT / "profiles" / "roofline_traffic.json", "w"), indent=1)

@@ -72,6 +72,21 @@ def build_pb2(force: bool = False) -> Path:
     return out
 
 
+def build_kat(force: bool = False) -> Path:
+    """libpb2_kat.so: the per-function known-answer hooks of the -m gpu tests (csrc/test_hooks/kat.cu, include/pb2_kat.h).
+    Test infrastructure, kept out of the product library; it links against libpb2.so for the record conversions."""
+    BUILD.mkdir(exist_ok=True)
+    out, src, obj = BUILD / "libpb2_kat.so", CSRC / "test_hooks" / "kat.cu", BUILD / "kat.o"
+    hdrs = sorted(CSRC.glob("*.cuh")) + [ROOT / "include" / "pb2.h", ROOT / "include" / "pb2_kat.h"]
+    if force or _newer(obj, [src, *hdrs]):
+        extra = FAST_SHADING_FLAGS if "PB2_IEEE_SHADING" not in os.environ else []
+        _run([NVCC, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)], BUILD / "kat.ptxas.log")
+    if force or _newer(out, [obj, BUILD / "libpb2.so"]):
+        _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", str(obj), "-o", str(out), f"-L{BUILD}", "-lpb2", "-lcudart",
+              "-Xlinker", "-rpath,$ORIGIN"])
+    return out
+
+
 def build_host(force: bool = False) -> Path:
     """libpupil_host.so (the C++ host surface + its C entry points) and the headless path_tracer executable."""
     BUILD.mkdir(exist_ok=True)
@@ -88,6 +103,7 @@ def build_host(force: bool = False) -> Path:
 
 def build_all(force: bool = False) -> None:
     build_pb2(force)
+    build_kat(force)
     build_host(force)
 
 

@@ -430,6 +430,25 @@ bool sah_builder_available();
 void build_binary_sah(cudaStream_t st, uint32_t n, const float4 *box_lo, const float4 *box_hi, const uint32_t *sorted, int *left, int *right, int2 *range,
                       float4 *lo, float4 *hi);
 
+// largest vertex index of an index buffer (pb2_scene_add_mesh rejects meshes that point past their vertex arrays)
+__global__ void __launch_bounds__(256) k_max_index(const uint32_t *__restrict__ idx, uint64_t n, uint32_t *__restrict__ out) {
+    uint32_t m = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) m = max(m, __ldg(idx + i));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31u) == 0u) atomicMax(out, m);
+}
+uint32_t max_index_dev(const uint32_t *idx, uint64_t n, cudaStream_t st) {
+    if (!n) return 0;
+    DevBuf<uint32_t> d(1);
+    d.zero(st);
+    k_max_index<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(idx, n, d.ptr);
+    PB2_LAUNCH_CHECK();
+    uint32_t h = 0;
+    PB2_CUDA(cudaMemcpyAsync(&h, d.ptr, sizeof h, cudaMemcpyDeviceToHost, st));
+    PB2_CUDA(cudaStreamSynchronize(st));
+    return h;
+}
+
 void build_bvh(Scene &s) {
     cudaStream_t st = s.stream;
     s.upload_tables();

@@ -78,6 +78,7 @@ Scene::Scene() {
 }
 Scene::~Scene() {
     if (wf) wavefront_destroy(wf);
+    if (accumulate_gate) cudaEventDestroy(accumulate_gate);
     if (own_stream) cudaStreamDestroy(own_stream);
 }
 void Scene::apply_l2_window() {
@@ -130,6 +131,15 @@ void Scene::upload_tables() {
     if (has_env) d_env.upload(&h_env, 1, stream);
     PB2_CUDA(cudaStreamSynchronize(stream)); // host vectors may change right after
     tables_dirty = false;
+}
+void Scene::check_emitter_ranges() const {
+    for (size_t i = 0; i < h_inst.size(); ++i) {
+        const DevInstance &in = h_inst[i];
+        if (in.emitter_offset >= 0 && (uint64_t)in.emitter_offset + in.n_tris > h_areas.size())
+            throw std::runtime_error("pb2_render: instance " + std::to_string(i) + " names emitter entries [" + std::to_string(in.emitter_offset) + ", " +
+                                     std::to_string((uint64_t)in.emitter_offset + in.n_tris) + ") but the emitter table holds " + std::to_string(h_areas.size()) +
+                                     " (pb2_scene_set_emitters)");
+    }
 }
 SceneView Scene::view() const {
     SceneView v{};
@@ -411,7 +421,9 @@ int pb2_scene_add_mesh(pb2_scene *scene, const float *pos, const float *nrm, con
     if (nrm) m->nrm.upload(nrm, (size_t)n_vertices * 3, s.stream);
     if (uv) m->uv.upload(uv, (size_t)n_vertices * 2, s.stream);
     m->idx.upload(idx, (size_t)n_triangles * 3, s.stream);
-    PB2_CUDA(cudaStreamSynchronize(s.stream)); // caller may free its arrays now
+    // an index past the vertex arrays would be an out-of-bounds device read in every kernel that touches the mesh
+    const uint32_t max_idx = max_index_dev(m->idx.ptr, (uint64_t)n_triangles * 3, s.stream); // synchronises: caller may free its arrays now
+    if (max_idx >= n_vertices) return fail(PB2_ERR_ARG, "pb2_scene_add_mesh: vertex index " + std::to_string(max_idx) + " >= n_vertices " + std::to_string(n_vertices));
     if (mesh_id) *mesh_id = (uint32_t)s.meshes.size();
     s.meshes.push_back(std::move(m));
     return PB2_OK;
@@ -590,17 +602,66 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     else return fail(PB2_ERR_ARG, "pb2_scene_set_option: unknown option " + n);
     return PB2_OK;
 }
+// ---- multi-GPU (comm.cu) ----
+int pb2_comm_unique_id(uint8_t id[PB2_COMM_ID_BYTES]) {
+    PB2_TRY
+    if (!id) return fail(PB2_ERR_ARG, "pb2_comm_unique_id: null");
+    comm_unique_id(id);
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_comm_create(pb2_comm **comm, int n_ranks, int rank, const uint8_t id[PB2_COMM_ID_BYTES]) {
+    PB2_TRY
+    if (!comm) return fail(PB2_ERR_ARG, "pb2_comm_create: null");
+    *comm = reinterpret_cast<pb2_comm *>(comm_create(n_ranks, rank, id));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_comm_destroy(pb2_comm *comm) {
+    PB2_TRY
+    comm_destroy(reinterpret_cast<Comm *>(comm));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_comm_reduce_frames(pb2_comm *comm, pb2_scene *scene, const void *sum_buffer, void *frame_buffer, uint64_t n_pixels, uint32_t total_spp, int mode, int root) {
+    PB2_TRY
+    if (!comm || !scene) return fail(PB2_ERR_ARG, "pb2_comm_reduce_frames: null");
+    if (mode != PB2_REDUCE_ROOT && mode != PB2_REDUCE_ALL) return fail(PB2_ERR_ARG, "pb2_comm_reduce_frames: mode is PB2_REDUCE_ROOT or PB2_REDUCE_ALL");
+    comm_reduce_frames(*reinterpret_cast<Comm *>(comm), *S(scene), static_cast<const float4 *>(sum_buffer), static_cast<float4 *>(frame_buffer), n_pixels, total_spp, mode, root);
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_comm_synchronize(pb2_comm *comm) {
+    PB2_TRY
+    if (!comm) return fail(PB2_ERR_ARG, "pb2_comm_synchronize: null");
+    comm_synchronize(*reinterpret_cast<Comm *>(comm));
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_comm_nccl_version(int *version) {
+    PB2_TRY
+    if (!version) return fail(PB2_ERR_ARG, "pb2_comm_nccl_version: null");
+    *version = comm_nccl_version();
+    return PB2_OK;
+    PB2_CATCH
+}
+// rank r of N renders the seeds base + r + k N.  weak: every rank renders `spp` frames per step (the step
+// covers spp * N seeds); strong: the step's `spp` frames are split, rank r takes ceil((spp - r) / N) of them.
+int pb2_shard_plan(int rank, int n_ranks, uint32_t step, uint32_t spp, int strong, uint32_t *first_seed, uint32_t *seed_stride, uint32_t *spp_rank, uint32_t *spp_total) {
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || spp < 1) return fail(PB2_ERR_ARG, "pb2_shard_plan: bad rank / size / spp");
+    const uint32_t n = (uint32_t)n_ranks, r = (uint32_t)rank;
+    const uint32_t total = strong ? spp : spp * n;
+    if (first_seed) *first_seed = step * total + r;
+    if (seed_stride) *seed_stride = n;
+    if (spp_rank) *spp_rank = strong ? (spp > r ? (spp - r + n - 1) / n : 0u) : spp;
+    if (spp_total) *spp_total = total;
+    return PB2_OK;
+}
 int pb2_finalize_sum(pb2_scene *scene, const void *sum_buffer, void *frame_buffer, uint64_t n_pixels, uint32_t total_spp) {
     PB2_TRY
     if (!scene || !sum_buffer || !frame_buffer || !total_spp) return fail(PB2_ERR_ARG, "pb2_finalize_sum: bad argument");
     finalize_sum(*S(scene), static_cast<const float4 *>(sum_buffer), static_cast<float4 *>(frame_buffer), n_pixels, total_spp);
     return PB2_OK;
-    PB2_CATCH
-}
-int pb2_kat(const char *what, const void *in0, const void *in1, const void *in2, uint64_t n, void *out) {
-    PB2_TRY
-    if (!what || !out) return fail(PB2_ERR_ARG, "pb2_kat: null");
-    return run_kat(what, in0, in1, in2, n, out);
     PB2_CATCH
 }
 }

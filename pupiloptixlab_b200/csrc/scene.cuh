@@ -68,15 +68,21 @@ struct Scene {
 
     Wavefront *wf = nullptr;
     pb2_render_stats render_stats{};
+    // recorded by pb2_comm_reduce_frames on the communicator's stream while it reads the sum buffer; the next k_accumulate
+    // (the only writer of that buffer) waits for it, everything before it overlaps the reduction (comm.cu)
+    cudaEvent_t accumulate_gate = nullptr;
+    bool gate_pending = false;
 
     Scene();
     ~Scene();
     void upload_tables();
+    void check_emitter_ranges() const; // every emitting instance's [offset, offset + n_tris) lies inside the emitter table (throws)
     SceneView view() const;
 };
 
 // bvh_build.cu
 void build_bvh(Scene &s);
+uint32_t max_index_dev(const uint32_t *idx, uint64_t n, cudaStream_t st);
 // trace.cu
 void trace_closest_dev(Scene &s, const float4 *rays, uint64_t n, float4 *hit_tuvp, int32_t *hit_inst);
 void trace_any_dev(Scene &s, const float4 *rays, uint64_t n, uint32_t *occluded);
@@ -84,6 +90,14 @@ void trace_any_dev(Scene &s, const float4 *rays, uint64_t n, uint32_t *occluded)
 void render(Scene &s, const pb2_launch_params &p);
 void finalize_sum(Scene &s, const float4 *sum, float4 *frame, uint64_t n, uint32_t spp);
 void wavefront_destroy(Wavefront *wf);
-// kat.cu
+// comm.cu
+struct Comm;
+void comm_unique_id(uint8_t id[PB2_COMM_ID_BYTES]);
+Comm *comm_create(int n_ranks, int rank, const uint8_t *id);
+void comm_destroy(Comm *c);
+void comm_reduce_frames(Comm &c, Scene &s, const float4 *sum, float4 *frame, uint64_t n_pixels, uint32_t total_spp, int mode, int root);
+void comm_synchronize(Comm &c);
+int comm_nccl_version();
+// test_hooks/kat.cu (libpb2_kat.so, not part of libpb2.so)
 int run_kat(const char *what, const void *in0, const void *in1, const void *in2, uint64_t n, void *out);
 }// namespace pb2

@@ -1,6 +1,6 @@
 // Per-function known-answer hooks (pb2_kat): run the DEVICE restatement of one reference function over n
-// inputs so tests can compare it with the oracle on the same grids.  Test-only entry point; not on the
-// render path.  All arrays are HOST pointers; layouts:
+// inputs so tests can compare it with the oracle on the same grids.  Test-only entry point, built into its own
+// library (libpb2_kat.so, include/pb2_kat.h): the product library libpb2.so does not contain it.  All arrays are HOST pointers; layouts:
 //   "rng"      in0 uint32[n][3] (rounds, v0, v1)                       out uint32/float[n][8]  state, 7 draws
 //   "warp"     in0 float[n][2]  (u1,u2)                                out float[n][12] tri, sphere, coshemi, unihemi
 //   "frame"    in0 float[n][6]  (v, N)                                 out float[n][8]  to_local, to_world, sphere_uv(N)
@@ -11,8 +11,9 @@
 //   "emitter"  in0 pb2_emitter[n], in1 float[n][8] (hit_pos, hit_n, xi), in2 float[n][12] (emit_pos, emit_n, uv, scatter)
 //                                                                      out float[n][16] sample: radiance wi distance pdf | eval: radiance pdf
 //   "select"   in0 pb2_emitter[m] (m = in2[0] as uint32, has_env = in2[1]), in1 float[n] p   out int32[n] index (m = env, -1 none)
-#include "scene.cuh"
-#include "pt_math.cuh"
+#include "../scene.cuh"
+#include "../pt_math.cuh"
+#include "../../../include/pb2_kat.h"
 #include <cstring>
 #include <string>
 #include <vector>
@@ -218,3 +219,26 @@ int run_kat(const char *what_c, const void *in0, const void *in1, const void *in
     throw std::runtime_error("pb2_kat: unknown function '" + what + "'");
 }
 }// namespace pb2
+
+// the C entry point of libpb2_kat.so (include/pb2_kat.h); errors are reported through its own message slot
+namespace {
+thread_local std::string g_kat_error;
+}
+extern "C" {
+const char *pb2_kat_last_error(void) { return g_kat_error.c_str(); }
+int pb2_kat(const char *what, const void *in0, const void *in1, const void *in2, uint64_t n, void *out) {
+    if (!what || !out) {
+        g_kat_error = "pb2_kat: null";
+        return PB2_ERR_ARG;
+    }
+    try {
+        return pb2::run_kat(what, in0, in1, in2, n, out);
+    } catch (const pb2::CudaError &e) {
+        g_kat_error = e.what();
+        return PB2_ERR_CUDA;
+    } catch (const std::exception &e) {
+        g_kat_error = e.what();
+        return PB2_ERR_STATE;
+    }
+}
+}

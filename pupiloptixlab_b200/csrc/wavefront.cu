@@ -609,8 +609,9 @@ __global__ void k_collect_counts(const uint32_t *__restrict__ counters, uint32_t
 __global__ void __launch_bounds__(256) k_accumulate(const float4 *__restrict__ rad, uint32_t n_pixels, uint32_t frames, uint32_t mode, uint32_t sample_cnt0,
                                                     float4 *__restrict__ accum, float4 *__restrict__ frame_buf) {
     for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < n_pixels; px += gridDim.x * blockDim.x) {
-        float3 acc = (mode != 0 && (sample_cnt0 > 0 || mode == 2)) ? mk3(accum[px]) : mk3(0.f);
-        float w = mode == 2 ? accum[px].w : 1.f;
+        // sample_cnt0 == 0 starts over in both accumulating modes: the buffer's previous content is not read
+        float3 acc = (mode != 0 && sample_cnt0 > 0) ? mk3(accum[px]) : mk3(0.f);
+        float w = mode == 2 ? (sample_cnt0 > 0 ? accum[px].w : 0.f) : 1.f;
         for (uint32_t f = 0; f < frames; ++f) {
             const float3 r = mk3(rad[(size_t)f * n_pixels + px]);
             if (mode == 2) { // plain sum for sample-sharded multi-GPU rendering
@@ -639,16 +640,18 @@ __global__ void k_finalize_sum(const float4 *__restrict__ sum, float4 *__restric
 }
 }// namespace
 
-void finalize_sum(Scene &s, const float4 *sum, float4 *frame, uint64_t n, uint32_t spp) {
+void finalize_sum_on(cudaStream_t st, const float4 *sum, float4 *frame, uint64_t n, uint32_t spp) {
     if (!n) return;
-    k_finalize_sum<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, s.stream>>>(sum, frame, n, 1.f / (float)spp);
+    k_finalize_sum<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(sum, frame, n, 1.f / (float)spp);
     PB2_LAUNCH_CHECK();
 }
+void finalize_sum(Scene &s, const float4 *sum, float4 *frame, uint64_t n, uint32_t spp) { finalize_sum_on(s.stream, sum, frame, n, spp); }
 
 void render(Scene &s, const pb2_launch_params &lp) {
     if (!s.bvh_valid) throw std::runtime_error("pb2_render: call pb2_bvh_build first");
     if (!lp.accum_buffer || !lp.width || !lp.height) throw std::runtime_error("pb2_render: accum_buffer / width / height missing");
     if (lp.max_depth > 0xffffu) throw std::runtime_error("pb2_render: max_depth too large");
+    s.check_emitter_ranges();
     s.upload_tables();
     if (!s.wf) s.wf = new Wavefront();
     Wavefront &wf = *s.wf;
@@ -809,6 +812,10 @@ void render(Scene &s, const pb2_launch_params &lp) {
         // batches fold into the image in frame order (the running mean of main.cu:190-196 depends on it): wait for the
         // previous batch's accumulate, which ran on the other lane
         if (batch > 0 && n_lanes == 2) PB2_CUDA(cudaStreamWaitEvent(st, wf.lane[(batch - 1) % n_lanes].accumulated, 0));
+        if (s.gate_pending) { // a multi-GPU reduction is still reading the accumulation buffer (comm.cu): this is its only writer
+            PB2_CUDA(cudaStreamWaitEvent(st, s.accumulate_gate, 0));
+            s.gate_pending = false;
+        }
         stage_begin(4);
         k_accumulate<<<(unsigned)std::min<uint64_t>((n_pixels + 255) / 256, (uint64_t)sms * 8), 256, 0, st>>>(
             ln.rad.ptr, n_pixels, frames, lp.accumulate, sample_cnt, (float4 *)lp.accum_buffer, (float4 *)lp.frame_buffer);
@@ -816,7 +823,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
         stage_end();
         if (n_lanes == 2) PB2_CUDA(cudaEventRecord(ln.accumulated, st));
         ++wf.launches;
-        if (lp.accumulate == 1) sample_cnt += frames;
+        if (lp.accumulate != 0) sample_cnt += frames;
         k_collect_counts<<<1, 32, 0, st>>>(ln.counters.ptr, rounds, wf.ray_totals.ptr);
         PB2_LAUNCH_CHECK();
         ++wf.launches;

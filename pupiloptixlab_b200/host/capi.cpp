@@ -12,6 +12,11 @@ using namespace Pupil;
 namespace {
 std::string g_error;
 std::unique_ptr<pt::PTPass> g_pass;
+pb2_comm *g_comm = nullptr; // the communicator of pupil_set_shard (owned here; the pass borrows it)
+int g_rank = 0, g_world = 1, g_reduce_mode = PB2_REDUCE_ALL;
+void SyncIfSharded() {
+    if (g_pass && g_pass->IsSharded()) g_pass->Synchronize(); // a sharded OnRun returns before the reduction has finished
+}
 int Fail(const std::string &m) {
     g_error = m;
     return 1;
@@ -38,6 +43,8 @@ int pupil_init(int device) {
     return 0;
 }
 int pupil_shutdown(void) {
+    if (g_pass) g_pass->SetShard(nullptr, 0, 1, false, PB2_REDUCE_ALL);
+    if (g_comm) pb2_comm_destroy(g_comm), g_comm = nullptr;
     if (g_pass) Sys()->RemovePass(g_pass.get());
     g_pass.reset();
     if (Sys()->IsInitialized()) Sys()->Destroy();
@@ -46,16 +53,17 @@ int pupil_shutdown(void) {
 int pupil_load_scene_xml(const char *path) {
     if (!Ready()) return Fail("pupil_init first");
     if (!path || !std::filesystem::exists(path)) return Fail(std::string("scene file does not exist: ") + (path ? path : "(null)"));
-    Sys()->SetScene(std::filesystem::path(path));
-    if (!g_pass->GetLaunchParams().accum_buffer) return Fail("scene load failed");
+    if (!Sys()->SetScene(std::filesystem::path(path)) || !g_pass->GetLaunchParams().accum_buffer) return Fail("scene load failed");
     return 0;
 }
 int pupil_load_scene_xml_string(const char *xml, const char *root_dir) {
     if (!Ready()) return Fail("pupil_init first");
     if (!xml) return Fail("null xml");
-    if (!W()->scene->LoadFromXMLString(xml, root_dir ? std::filesystem::path(root_dir) : std::filesystem::path())) return Fail("XML parse failed");
-    Sys()->SetScene(W()->scene.get());
-    if (!g_pass->GetLaunchParams().accum_buffer) return Fail("scene load failed");
+    if (!W()->scene->LoadFromXMLString(xml, root_dir ? std::filesystem::path(root_dir) : std::filesystem::path())) {
+        Sys()->SetScene(static_cast<resource::Scene *>(nullptr)); // fails, and clears what the previous scene left behind
+        return Fail("XML parse failed");
+    }
+    if (!Sys()->SetScene(W()->scene.get()) || !g_pass->GetLaunchParams().accum_buffer) return Fail("scene load failed");
     return 0;
 }
 int pupil_parse_scene_xml(const char *path) {
@@ -102,6 +110,7 @@ int pupil_save_buffer(const char *name, const char *path, int format) {
     if (!Ready() || !name || !path || format < 0 || format > 4) return Fail("pupil_save_buffer: bad arguments / no scene");
     Buffer *b = util::Singleton<BufferManager>::instance()->GetBuffer(name);
     if (!b || !b->cuda_ptr || b->desc.stride_in_byte != 16) return Fail("pupil_save_buffer: no such float4 buffer");
+    SyncIfSharded();
     std::vector<float> host(static_cast<size_t>(b->desc.width) * b->desc.height * 4);
     if (pb2_download(host.data(), b->cuda_ptr, host.size() * sizeof(float)) != PB2_OK) return Fail(pb2_last_error());
     const util::DisplayTransform display{ format == 4, true };
@@ -129,6 +138,13 @@ int pupil_set_instance_transform(uint32_t index, const float xform[16]) {
     ro->UpdateTransform(t); // EWorldEvent::RenderInstanceTransform -> emitters reset, acceleration structure dirty, pass restarts
     return 0;
 }
+int pupil_remove_instance(uint32_t index) {
+    if (!HasWorld()) return Fail("no scene");
+    if (!W()->GetRenderObject(static_cast<size_t>(index))) return Fail("no such render object");
+    W()->RemoveRenderObject(static_cast<size_t>(index)); // World::RemoveRenderObject: its emitters leave the table with it
+    EventDispatcher<EWorldEvent::RenderInstanceUpdate>(nullptr); // the pass restarts its accumulation
+    return 0;
+}
 int pupil_clear_shapes(void) {
     util::Singleton<resource::ShapeManager>::instance()->Clear();
     return 0;
@@ -140,6 +156,27 @@ int pupil_pass_config(int max_depth, int accumulate, uint32_t frames_per_run, ui
     g_pass->SetFramesPerRun(frames_per_run);
     g_pass->SetSumMode(sum_mode != 0);
     g_pass->Restart(first_seed, seed_stride);
+    return 0;
+}
+int pupil_comm_unique_id(uint8_t id[PB2_COMM_ID_BYTES]) { return pb2_comm_unique_id(id) == PB2_OK ? 0 : Fail(pb2_last_error()); }
+int pupil_set_shard(int rank, int world, const uint8_t *id, int strong, int reduce_mode) {
+    if (!Ready()) return Fail("pupil_init first");
+    g_pass->SetShard(nullptr, 0, 1, false, PB2_REDUCE_ALL);
+    if (g_comm) pb2_comm_destroy(g_comm), g_comm = nullptr;
+    if (world <= 0) return 0; // sharding off
+    if (pb2_comm_create(&g_comm, world, rank, id) != PB2_OK) return Fail(pb2_last_error());
+    g_rank = rank, g_world = world, g_reduce_mode = reduce_mode;
+    g_pass->SetShard(g_comm, rank, world, strong != 0, reduce_mode);
+    return 0;
+}
+int pupil_set_shard_plan(int strong) {
+    if (!Ready() || !g_comm) return Fail("pupil_set_shard first");
+    g_pass->SetShard(g_comm, g_rank, g_world, strong != 0, g_reduce_mode); // same communicator, other split of the step's seeds
+    return 0;
+}
+int pupil_synchronize(void) {
+    if (!Ready()) return Fail("pupil_init first");
+    g_pass->Synchronize();
     return 0;
 }
 int pupil_run(uint64_t n) {
@@ -173,6 +210,7 @@ int pupil_buffer_info(const char *name, void **dptr, uint32_t *w, uint32_t *h, u
     return 0;
 }
 int pupil_buffer_download(const char *name, void *host, uint64_t bytes) {
+    SyncIfSharded();
     Buffer *b = name ? util::Singleton<BufferManager>::instance()->GetBuffer(name) : nullptr;
     if (!b) return Fail(std::string("no buffer named ") + (name ? name : "(null)"));
     if (bytes > b->SizeInBytes()) return Fail("buffer is smaller than the request");
@@ -207,13 +245,8 @@ int pupil_get_instance(uint32_t index, float xform[16], pb2_material *material, 
     if (!HasWorld()) return Fail("no scene");
     auto ros = W()->GetRenderobjects();
     if (index >= ros.size()) return Fail("instance index out of range");
-    int offset = 0, mine = -1;
-    for (uint32_t i = 0; i <= index; ++i)
-        if (ros[i]->is_emitter) {
-            if (i == index) mine = offset;
-            offset += (int)ros[i]->sub_emitters_num;
-        }
     const world::RenderObject *ro = ros[index];
+    const int mine = W()->GetEmitterOffset(ro);
     if (xform) std::memcpy(xform, ro->transform.matrix.e, 64);
     if (material) *material = ro->mat;
     if (emitter_offset) *emitter_offset = mine;

@@ -1,6 +1,7 @@
 #include "pt_pass.h"
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -26,12 +27,16 @@ void PTPass::OnRun() noexcept {
         m_params.config.accumulated_flag = m_accumulated_flag;
         m_params.sample_cnt = 0;
         m_params.random_seed = m_first_seed;
-        if (m_sum_mode) pb2_memset(m_params.accum_buffer, 0, m_output_pixel_num * sizeof(float) * 4); // sums start from zero
+        m_shard_step = 0, m_shard_total_spp = 0; // sums start over: accumulate = 2 with sample_cnt = 0 does not read the buffer
         m_dirty = false;
     }
     m_params.handle = m_world->GetSceneHandle(); // refreshes BVH / camera / emitters when they changed
     if (!m_params.handle) return;
 
+    if (m_comm) {
+        OnRunSharded();
+        return;
+    }
     pb2_launch_params lp{};
     lp.max_depth = m_params.config.max_depth;
     lp.accumulate = m_sum_mode ? 2u : (m_params.config.accumulated_flag ? 1u : 0u);
@@ -48,7 +53,53 @@ void PTPass::OnRun() noexcept {
     m_params.random_seed += m_frames_per_run * m_seed_stride;                                // :56
 }
 
+// One progressive step of a sharded render: this rank's seeds into the sum buffer, then the asynchronous reduction.
+void PTPass::OnRunSharded() noexcept {
+    uint32_t first = 0, stride = 1, mine = 0, total = 0;
+    if (pb2_shard_plan(m_rank, m_n_ranks, m_shard_step, m_frames_per_run, m_strong ? 1 : 0, &first, &stride, &mine, &total) != PB2_OK) {
+        Log::Error("pb2_shard_plan: %s", pb2_last_error());
+        return;
+    }
+    pb2_launch_params lp{};
+    lp.max_depth = m_params.config.max_depth;
+    lp.accumulate = 2u;
+    lp.width = m_params.config.frame.width, lp.height = m_params.config.frame.height;
+    lp.random_seed = m_first_seed + first, lp.seed_stride = stride;
+    lp.sample_cnt = m_params.sample_cnt, lp.n_frames = mine;
+    lp.accum_buffer = m_params.accum_buffer, lp.frame_buffer = nullptr;
+    lp.normal_buffer = m_params.normal_buffer, lp.albedo_buffer = m_params.albedo_buffer, lp.test_buffer = m_params.test;
+    if (mine > 0) {
+        if (pb2_render(m_params.handle, &lp) != PB2_OK) {
+            Log::Error("pb2_render: %s", pb2_last_error());
+            return;
+        }
+    } else if (m_params.sample_cnt == 0) { // more ranks than samples: this rank contributes zeros
+        Synchronize();
+        pb2_memset(m_params.accum_buffer, 0, m_output_pixel_num * sizeof(float) * 4);
+    }
+    m_params.sample_cnt += mine, m_shard_total_spp += total, ++m_shard_step;
+    m_params.random_seed = m_first_seed + m_shard_step * total;
+    if (pb2_comm_reduce_frames(m_comm, m_params.handle, m_params.accum_buffer, m_params.frame_buffer, m_output_pixel_num, m_shard_total_spp, m_reduce_mode, 0) != PB2_OK)
+        Log::Error("pb2_comm_reduce_frames: %s", pb2_last_error());
+}
+void PTPass::SetShard(pb2_comm *comm, int rank, int world, bool strong, int reduce_mode) noexcept {
+    Synchronize();
+    m_comm = comm, m_rank = rank, m_n_ranks = world > 0 ? world : 1, m_strong = strong, m_reduce_mode = reduce_mode;
+    m_dirty = true;
+}
+void PTPass::Synchronize() noexcept {
+    if (m_params.handle) pb2_synchronize(m_params.handle);
+    if (m_comm) pb2_comm_synchronize(m_comm);
+}
+
 void PTPass::SetScene(world::World *world) noexcept {
+    if (world == nullptr) { // a scene load failed (System::AfterSceneLoadFailed): nothing to render until the next SetScene
+        m_world = nullptr;
+        m_params = LaunchParams{};
+        m_output_pixel_num = 0;
+        m_dirty = true;
+        return;
+    }
     m_world = world;
     m_params.config.frame.width = world->scene->sensor.film.w;
     m_params.config.frame.height = world->scene->sensor.film.h;
@@ -115,10 +166,35 @@ struct CheckpointHeader { // little-endian, 64 bytes
     char magic[8];        // "PB2CKPT1"
     uint32_t width, height, max_depth, accumulate, sum_mode;
     uint32_t sample_cnt, random_seed, first_seed, seed_stride, frames_per_run;
-    uint32_t reserved[4];
+    uint32_t scene_hash[2]; // SceneFingerprint(): 0, 0 in files written before the fingerprint existed (accepted)
+    uint32_t reserved[2];
 };
 static_assert(sizeof(CheckpointHeader) == 64);
 constexpr char kCheckpointMagic[8] = { 'P', 'B', '2', 'C', 'K', 'P', 'T', '1' };
+// FNV-1a over what decides the image besides the seeds: camera matrices, every render object's transform, geometry size,
+// flags and material (values, not device handles), the emitter table's weights and the integrator depth is in the header
+// already.  A checkpoint of another scene or of other camera / instance edits at the same resolution is refused.
+uint64_t SceneFingerprint(world::World *w) {
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *p, size_t n) {
+        const unsigned char *b = static_cast<const unsigned char *>(p);
+        for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    const util::Mat4 s2c = w->camera->GetSampleToCameraMatrix(), c2w = w->camera->GetToWorldMatrix();
+    mix(s2c.e, sizeof s2c.e), mix(c2w.e, sizeof c2w.e);
+    for (world::RenderObject *ro : w->GetRenderobjects()) {
+        mix(ro->transform.matrix.e, sizeof ro->transform.matrix.e);
+        const uint32_t geo[4] = { (uint32_t)ro->geo_type, ro->sub_emitters_num, (uint32_t)ro->flip_normals | (uint32_t)ro->flip_tex_coords << 1 | (uint32_t)ro->is_emitter << 2,
+                                  ro->shape && ro->geo_type == world::RenderObject::EGeoType::TriMesh ? ro->shape->mesh.vertex_num : 0u };
+        mix(geo, sizeof geo);
+        const pb2_material &m = ro->mat;
+        mix(&m.type, 24); // type, twosided, eta, nonlinear, int_fdr, specular_sampling_weight
+        for (const pb2_texture &t : m.tex) mix(&t, offsetof(pb2_texture, pad0)); // type, a, b, r0, r1 — not the bitmap handle
+    }
+    for (const pb2_emitter &e : w->emitters->GetAreaEmitters()) mix(&e.type, 12), mix(&e.area, sizeof e.area);
+    if (const pb2_emitter *env = w->emitters->GetEnvEmitter()) mix(&env->type, 12), mix(env->radiance.a, sizeof env->radiance.a);
+    return h;
+}
 }// namespace
 
 bool PTPass::SaveCheckpoint(const std::filesystem::path &file) noexcept {
@@ -127,7 +203,7 @@ bool PTPass::SaveCheckpoint(const std::filesystem::path &file) noexcept {
             Log::Warn("checkpoint: no scene to save");
             return false;
         }
-        if (m_params.handle) pb2_synchronize(m_params.handle);
+        Synchronize();
         CheckpointHeader h{};
         std::memcpy(h.magic, kCheckpointMagic, 8);
         h.width = m_params.config.frame.width, h.height = m_params.config.frame.height;
@@ -137,6 +213,8 @@ bool PTPass::SaveCheckpoint(const std::filesystem::path &file) noexcept {
         h.sum_mode = m_sum_mode ? 1u : 0u;
         h.sample_cnt = m_dirty ? 0u : m_params.sample_cnt, h.random_seed = m_dirty ? m_first_seed : m_params.random_seed;
         h.first_seed = m_first_seed, h.seed_stride = m_seed_stride, h.frames_per_run = m_frames_per_run;
+        const uint64_t fp = SceneFingerprint(m_world);
+        h.scene_hash[0] = (uint32_t)fp, h.scene_hash[1] = (uint32_t)(fp >> 32);
         std::vector<float> accum(m_output_pixel_num * 4), frame(m_output_pixel_num * 4);
         if (pb2_download(accum.data(), m_params.accum_buffer, accum.size() * sizeof(float)) != PB2_OK ||
             pb2_download(frame.data(), m_params.frame_buffer, frame.size() * sizeof(float)) != PB2_OK) {
@@ -185,6 +263,13 @@ bool PTPass::LoadCheckpoint(const std::filesystem::path &file) noexcept {
                       m_params.config.frame.height);
             ok = false;
         }
+        if (ok && (h.scene_hash[0] | h.scene_hash[1])) {
+            const uint64_t fp = SceneFingerprint(m_world);
+            if (h.scene_hash[0] != (uint32_t)fp || h.scene_hash[1] != (uint32_t)(fp >> 32)) {
+                Log::Warn("checkpoint: %s was taken from another scene, camera or instance placement", file.string().c_str());
+                ok = false;
+            }
+        }
         ok = ok && std::fread(accum.data(), sizeof(float), accum.size(), f) == accum.size() && std::fread(frame.data(), sizeof(float), frame.size(), f) == frame.size();
         ok = ok && std::fgetc(f) == EOF; // nothing may follow
         std::fclose(f);
@@ -192,7 +277,7 @@ bool PTPass::LoadCheckpoint(const std::filesystem::path &file) noexcept {
             Log::Warn("checkpoint: %s is not a checkpoint of this scene", file.string().c_str());
             return false;
         }
-        if (m_params.handle) pb2_synchronize(m_params.handle);
+        Synchronize();
         if (pb2_upload(m_params.accum_buffer, accum.data(), accum.size() * sizeof(float)) != PB2_OK ||
             pb2_upload(m_params.frame_buffer, frame.data(), frame.size() * sizeof(float)) != PB2_OK) {
             Log::Error("checkpoint: %s", pb2_last_error());

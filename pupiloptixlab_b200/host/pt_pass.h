@@ -48,11 +48,20 @@ public:
     bool SaveCheckpoint(const std::filesystem::path &file) noexcept;
     bool LoadCheckpoint(const std::filesystem::path &file) noexcept;
     void SetSumMode(bool sum) noexcept { m_sum_mode = sum, m_dirty = true; } // accumulate plain sums (multi-GPU shards)
+    // Multi-GPU: this process is rank `rank` of `world`, one process per GPU.  Each OnRun renders this rank's
+    // share of the step's seeds (pb2_shard_plan; strong: frames_per_run is the step's TOTAL sample count, split over the
+    // ranks; weak: every rank renders frames_per_run) into plain sums and queues pb2_comm_reduce_frames, which leaves
+    // sum / total spp in "final result".  OnRun does not wait: the reduction overlaps the next OnRun's render up to its first
+    // accumulate kernel.  Synchronize() waits for both.  comm == nullptr switches sharding off.
+    void SetShard(pb2_comm *comm, int rank, int world, bool strong, int reduce_mode) noexcept;
+    void Synchronize() noexcept;
+    bool IsSharded() const noexcept { return m_comm != nullptr; }
     const LaunchParams &GetLaunchParams() const noexcept { return m_params; }
     pb2_render_stats GetRenderStats() noexcept;
 
 private:
     void BindingEventCallback() noexcept;
+    void OnRunSharded() noexcept;
     LaunchParams m_params;
     size_t m_output_pixel_num = 0;
     std::atomic_bool m_dirty = true;
@@ -60,5 +69,9 @@ private:
     int m_max_depth = 1;
     bool m_accumulated_flag = true, m_sum_mode = false;
     unsigned int m_frames_per_run = 1, m_first_seed = 0, m_seed_stride = 1;
+    pb2_comm *m_comm = nullptr; // not owned
+    int m_rank = 0, m_n_ranks = 1, m_reduce_mode = PB2_REDUCE_ALL;
+    bool m_strong = false;
+    unsigned int m_shard_step = 0, m_shard_total_spp = 0; // OnRun calls and samples of all ranks since the last restart
 };
 }// namespace Pupil::pt

@@ -591,6 +591,10 @@ void Scene::LoadXmlObj(const xml::Object *o, void *dst) noexcept {
             }
             xml::LoadInt(o, "width", film->w, 768);
             xml::LoadInt(o, "height", film->h, 576);
+            if (film->w <= 0 || film->h <= 0 || film->w > 65536 || film->h > 65536) { // uint32 casts and the aspect ratio follow
+                Log::Warn("film size %dx%d is not renderable: using 768x576", (int)film->w, (int)film->h);
+                film->w = 768, film->h = 576;
+            }
         } break;
         case xml::ETag::_sensor: {
             auto *s = static_cast<Sensor *>(dst);

@@ -105,16 +105,22 @@ void System::AfterSceneLoad() noexcept {
     m_scene_load_flag = true;
     EventDispatcher<ESystemEvent::SceneLoad>(static_cast<void *>(world));
 }
-void System::SetScene(std::filesystem::path scene_file_path) noexcept {
+void System::AfterSceneLoadFailed() noexcept {
+    util::Singleton<world::World>::instance()->Reset();
+    m_scene_load_flag = false;
+    EventDispatcher<ESystemEvent::SceneLoad>(nullptr); // passes drop the previous scene's buffers and handle
+}
+bool System::SetScene(std::filesystem::path scene_file_path) noexcept {
     if (!std::filesystem::exists(scene_file_path)) {
         Log::Warn("scene file [%s] does not exist", scene_file_path.string().c_str());
-        return;
+        return false;
     }
     {
         std::unique_lock render_lock(m_render_system_mutex);
         if (!util::Singleton<world::World>::instance()->LoadScene(scene_file_path)) {
             Log::Warn("scene load failed");
-            return;
+            AfterSceneLoadFailed();
+            return false;
         }
         AfterSceneLoad();
     }
@@ -123,15 +129,18 @@ void System::SetScene(std::filesystem::path scene_file_path) noexcept {
         EventDispatcher<ESystemEvent::Precompute>();
         EventDispatcher<ESystemEvent::StartRendering>();
     }
+    return true;
 }
-void System::SetScene(resource::Scene *scene) noexcept {
+bool System::SetScene(resource::Scene *scene) noexcept {
     std::unique_lock render_lock(m_render_system_mutex);
     if (!util::Singleton<world::World>::instance()->LoadScene(scene)) {
         Log::Warn("scene load failed");
-        return;
+        AfterSceneLoadFailed();
+        return false;
     }
     EventDispatcher<EWorldEvent::CameraChange>();
     AfterSceneLoad();
     render_flag = true;
+    return true;
 }
 }// namespace Pupil

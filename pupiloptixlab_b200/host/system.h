@@ -82,14 +82,18 @@ public:
     void Destroy() noexcept;
     void AddPass(Pass *pass) noexcept;
     void RemovePass(Pass *pass) noexcept;
-    void SetScene(std::filesystem::path scene_file_path) noexcept;
+    // The reference's SetScene returns nothing and carries on after a failed load (system.cpp:143-165); here the outcome is
+    // returned so that the C entry points can fail, and a failed load leaves NO scene behind (passes are told with a null
+    // SceneLoad event, the device scene is cleared) instead of the previous scene's buffers and geometry.
+    bool SetScene(std::filesystem::path scene_file_path) noexcept;
     // same hand-off for a scene assembled in memory (SceneDesc route): world->scene must already be filled
-    void SetScene(resource::Scene *scene) noexcept;
+    bool SetScene(resource::Scene *scene) noexcept;
     bool IsInitialized() const noexcept { return m_initialized; }
     uint64_t FramesRendered() const noexcept { return m_frames; }
 
 private:
     void AfterSceneLoad() noexcept;
+    void AfterSceneLoadFailed() noexcept;
     std::vector<Pass *> m_passes, m_pre_passes;
     Timer m_render_timer;
     bool m_initialized = false, m_scene_load_flag = false, m_system_run_flag = false;

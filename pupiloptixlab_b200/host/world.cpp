@@ -254,6 +254,11 @@ void EmitterHelper::ResetAreaEmitter(const resource::ShapeInstance &ins, size_t 
     else SetMeshAreaEmitter(ins, offset);
     m_dirty = true;
 }
+void EmitterHelper::RemoveAreaEmitters(size_t offset, size_t count) noexcept {
+    if (offset >= m_areas.size()) return;
+    m_areas.erase(m_areas.begin() + offset, m_areas.begin() + std::min(m_areas.size(), offset + count));
+    m_dirty = true;
+}
 void EmitterHelper::AddEmitter(const resource::Emitter &emitter) noexcept {
     if (emitter.type == resource::EEmitterType::ConstEnv) { // world/emitter.cpp:283-292
         m_env = pb2_emitter{};
@@ -386,6 +391,7 @@ bool World::LoadScene(std::filesystem::path path) noexcept {
     m_ros.clear();
     if (!scene->LoadFromXML(path) || !LoadScene(scene.get())) {
         Log::Error("scene load failed: %s", path.string().c_str());
+        Reset(); // the previous scene's geometry must not outlive a failed load
         return false;
     }
     timer.Stop();
@@ -437,7 +443,6 @@ void World::RebuildDeviceScene() noexcept {
     emitters->Invalidate(); // pb2_scene_clear drops the emitter table with the geometry
     if (m_builder >= 0) Pb2Check(pb2_scene_set_builder(m_pb2, m_builder), "pb2_scene_set_builder");
     std::unordered_map<uint32_t, uint32_t> mesh_of_shape;
-    int emitter_index_offset = 0;
     for (auto &ro : m_ros) {
         uint32_t mesh_id = PB2_MESH_SPHERE;
         if (ro->geo_type == RenderObject::EGeoType::TriMesh) {
@@ -451,8 +456,13 @@ void World::RebuildDeviceScene() noexcept {
             mesh_id = it->second;
         }
         const uint32_t flags = (ro->flip_normals ? PB2_INST_FLIP_NORMALS : 0u) | (ro->flip_tex_coords ? PB2_INST_FLIP_TEX : 0u);
+        // the offset EmitterHelper assigned when the object's emitters were added (kept current by RemoveRenderObject): the
+        // device table is EmitterHelper's table, so no second running sum here
         int offset = -1;
-        if (ro->is_emitter) offset = emitter_index_offset, emitter_index_offset += (int)ro->sub_emitters_num;
+        if (ro->is_emitter) {
+            auto it = m_ro_emitter_offset.find(ro.get());
+            if (it != m_ro_emitter_offset.end()) offset = (int)it->second;
+        }
         Pb2Check(pb2_scene_add_instance(m_pb2, mesh_id, ro->transform.matrix.e, flags, &ro->mat, offset, nullptr), "pb2_scene_add_instance");
     }
     Pb2Check(pb2_bvh_build(m_pb2, &m_build_stats), "pb2_bvh_build");
@@ -475,8 +485,28 @@ void World::RemoveRenderObject(size_t index) noexcept {
     if (index >= m_ros.size()) return;
     RenderObject *ro = m_ros[index].get();
     EventDispatcher<EWorldEvent::RenderInstanceRemove>(static_cast<void *>(ro));
+    // an emitting object takes its entries out of the emitter table with it: later objects move down by its entry count, and
+    // the selection probabilities are recomputed without the removed light
+    if (auto it = m_ro_emitter_offset.find(ro); it != m_ro_emitter_offset.end()) {
+        const size_t offset = it->second, count = ro->sub_emitters_num;
+        emitters->RemoveAreaEmitters(offset, count);
+        for (auto &kv : m_ro_emitter_offset)
+            if (kv.second > offset) kv.second -= count;
+        emitters->ComputeProbability();
+    }
     m_ro_emitter_offset.erase(ro), m_ro_in_scene_index.erase(ro);
     m_ros.erase(m_ros.begin() + index);
+    m_geometry_dirty = true;
+}
+int World::GetEmitterOffset(const RenderObject *ro) const noexcept {
+    auto it = m_ro_emitter_offset.find(ro);
+    return it == m_ro_emitter_offset.end() ? -1 : (int)it->second;
+}
+void World::Reset() noexcept {
+    m_ros.clear(), m_ro_emitter_offset.clear(), m_ro_in_scene_index.clear();
+    if (emitters) emitters->Clear();
+    if (m_pb2) Pb2Check(pb2_scene_clear(m_pb2), "pb2_scene_clear");
+    m_build_stats = pb2_build_stats{};
     m_geometry_dirty = true;
 }
 void World::UpdateRenderObject(RenderObject *) noexcept { m_geometry_dirty = true; }

@@ -61,6 +61,9 @@ public:
     void Clear() noexcept;
     size_t AddAreaEmitter(const resource::ShapeInstance &ins) noexcept; // returns the table size afterwards
     void ResetAreaEmitter(const resource::ShapeInstance &ins, size_t offset) noexcept;
+    // drops the table entries [offset, offset + count) of a removed render object (the caller shifts the later objects'
+    // offsets and calls ComputeProbability)
+    void RemoveAreaEmitters(size_t offset, size_t count) noexcept;
     void AddEmitter(const resource::Emitter &emitter) noexcept;
     void ComputeProbability() noexcept;
     const std::vector<pb2_emitter> &GetAreaEmitters() const noexcept { return m_areas; }
@@ -128,6 +131,10 @@ public:
     RenderObject *GetRenderObject(std::string_view name) const noexcept;
     RenderObject *GetRenderObject(size_t index) const noexcept;
     void RemoveRenderObject(size_t index) noexcept;
+    // first entry of the object's emitters in EmitterHelper's table (-1: not an emitter)
+    int GetEmitterOffset(const RenderObject *ro) const noexcept;
+    // a failed scene load leaves nothing behind: no render objects, no emitters, no device geometry
+    void Reset() noexcept;
     void UpdateRenderObject(RenderObject *ro) noexcept;
     std::vector<RenderObject *> GetRenderobjects() noexcept;
     void SetDirty() noexcept { m_geometry_dirty = true; }

@@ -87,11 +87,41 @@ struct Reader {
                     out.push_back(c), k += e.size() - 1, done = true;
                     break;
                 }
+            if (!done && k + 2 < v.size() && v[k + 1] == '#') { // numeric character reference: &#NN; / &#xHH; -> UTF-8
+                const bool hex = v[k + 2] == 'x' || v[k + 2] == 'X';
+                size_t j = k + (hex ? 3 : 2);
+                uint32_t cp = 0;
+                size_t digits = 0;
+                for (; j < v.size() && digits < 8; ++j, ++digits) {
+                    const char c = v[j];
+                    int d = (c >= '0' && c <= '9') ? c - '0' : (hex && c >= 'a' && c <= 'f') ? c - 'a' + 10 : (hex && c >= 'A' && c <= 'F') ? c - 'A' + 10 : -1;
+                    if (d < 0) break;
+                    cp = cp * (hex ? 16u : 10u) + (uint32_t)d;
+                }
+                if (digits > 0 && j < v.size() && v[j] == ';' && cp > 0 && cp <= 0x10FFFFu) {
+                    if (cp < 0x80) out.push_back((char)cp);
+                    else if (cp < 0x800) out.push_back((char)(0xC0 | cp >> 6)), out.push_back((char)(0x80 | (cp & 0x3F)));
+                    else if (cp < 0x10000) out.push_back((char)(0xE0 | cp >> 12)), out.push_back((char)(0x80 | (cp >> 6 & 0x3F))), out.push_back((char)(0x80 | (cp & 0x3F)));
+                    else out.push_back((char)(0xF0 | cp >> 18)), out.push_back((char)(0x80 | (cp >> 12 & 0x3F))), out.push_back((char)(0x80 | (cp >> 6 & 0x3F))), out.push_back((char)(0x80 | (cp & 0x3F)));
+                    k = j, done = true;
+                }
+            }
             if (!done) out.push_back('&');
         }
         return out;
     }
+    // Element() recurses once per nesting level: the depth is capped so that a hostile file fails instead of overflowing
+    // the stack (the dialect nests five or six levels deep)
+    static constexpr int kMaxDepth = 256;
+    int depth = 0;
     bool Element(Node &node) {
+        if (depth >= kMaxDepth) return Fail("elements nested deeper than " + std::to_string(kMaxDepth) + " levels");
+        ++depth;
+        const bool ok = ElementBody(node);
+        --depth;
+        return ok;
+    }
+    bool ElementBody(Node &node) {
         if (i >= s.size() || s[i] != '<') return Fail("expected '<'");
         ++i;
         node.name = Name();

@@ -99,7 +99,10 @@ def lib():
             "pb2_trace_closest_dev": [vp, vp, u64, vp, vp], "pb2_trace_any_dev": [vp, vp, u64, vp],
             "pb2_bvh_download": [vp, vp, P(u64), vp, P(u64)], "pb2_render": [vp, P(LaunchParams)], "pb2_synchronize": [vp],
             "pb2_render_stats_get": [vp, P(RenderStats)], "pb2_scene_set_option": [vp, C.c_char_p, C.c_int64],
-            "pb2_finalize_sum": [vp, vp, vp, u64, u32], "pb2_kat": [C.c_char_p, vp, vp, vp, u64, vp],
+            "pb2_finalize_sum": [vp, vp, vp, u64, u32],
+            "pb2_comm_unique_id": [vp], "pb2_comm_create": [P(vp), C.c_int, C.c_int, vp], "pb2_comm_destroy": [vp],
+            "pb2_comm_reduce_frames": [vp, vp, vp, vp, u64, u32, C.c_int, C.c_int], "pb2_comm_synchronize": [vp], "pb2_comm_nccl_version": [P(C.c_int)],
+            "pb2_shard_plan": [C.c_int, C.c_int, u32, u32, C.c_int, P(u32), P(u32), P(u32), P(u32)],
         }
         for name, args in sigs.items():
             fn = getattr(L, name)
@@ -289,5 +292,25 @@ def kat(what: str, in0, in1, in2, n: int, out: np.ndarray):
         if isinstance(x, np.ndarray):
             return _ptr(x)
         return C.cast(x, C.c_void_p)
-    check(lib().pb2_kat(what.encode(), p(in0), p(in1), p(in2), n, _ptr(out)))
+    code = kat_lib().pb2_kat(what.encode(), p(in0), p(in1), p(in2), n, _ptr(out))
+    if code != 0:
+        raise Pb2Error(f"pb2_kat error {code}: {kat_lib().pb2_kat_last_error().decode()}")
     return out
+
+
+_kat_lib = None
+
+
+def kat_lib():
+    """libpb2_kat.so: the known-answer test hooks (include/pb2_kat.h) — test infrastructure, not in libpb2.so"""
+    global _kat_lib
+    if _kat_lib is None:
+        lib()  # libpb2.so first: the hooks link against it
+        path = LIB_PATH.parent / "libpb2_kat.so"
+        if not path.exists():
+            raise Pb2Error(f"{path} not found: run `python -m pupiloptixlab_b200.build`")
+        L = C.CDLL(str(path))
+        L.pb2_kat.argtypes, L.pb2_kat.restype = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p], C.c_int
+        L.pb2_kat_last_error.restype = C.c_char_p
+        _kat_lib = L
+    return _kat_lib

@@ -56,6 +56,8 @@ def lib():
             "pupil_register_image": [C.c_char_p, vp, u32, u32], "pupil_image_load": [C.c_char_p, P(u32), P(u32), vp, u64],
             "pupil_image_save": [C.c_char_p, vp, u32, u32, C.c_int], "pupil_save_buffer": [C.c_char_p, C.c_char_p, C.c_int],
             "pupil_get_env_tables": [P(u32), P(u32), vp, vp, vp], "pupil_set_instance_transform": [u32, P(f32)],
+            "pupil_remove_instance": [u32], "pupil_comm_unique_id": [vp], "pupil_set_shard": [C.c_int, C.c_int, vp, C.c_int, C.c_int],
+            "pupil_synchronize": [], "pupil_set_shard_plan": [C.c_int],
             "pupil_checkpoint_save": [C.c_char_p], "pupil_checkpoint_load": [C.c_char_p],
         }
         for name, args in sigs.items():
@@ -126,6 +128,11 @@ def set_instance_transform(index: int, xform):
     check(lib().pupil_set_instance_transform(index, m.ctypes.data_as(C.POINTER(f32))))
 
 
+def remove_instance(index: int):
+    """World::RemoveRenderObject: the index-th render object leaves the scene, with its area emitters"""
+    check(lib().pupil_remove_instance(index))
+
+
 def image_load(path) -> np.ndarray:
     """util::BitmapTexture::Load: float32 (H, W, 4), row 0 = first row of the file; 8-bit sources linearised (gamma 2.2)"""
     w, h = u32(), u32()
@@ -159,6 +166,30 @@ def env_tables():
 def pass_config(max_depth: int = 0, accumulate: bool = True, frames_per_run: int = 1, first_seed: int = 0, seed_stride: int = 1,
                 sum_mode: bool = False):
     check(lib().pupil_pass_config(max_depth, int(accumulate), frames_per_run, first_seed, seed_stride, int(sum_mode)))
+
+
+REDUCE_ROOT, REDUCE_ALL = 0, 1
+
+
+def comm_unique_id() -> bytes:
+    """rank 0: the 128-byte NCCL id the other ranks need for set_shard (hand it over with any out-of-band channel)"""
+    buf = (C.c_uint8 * 128)()
+    check(lib().pupil_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def set_shard(rank: int, world: int, comm_id: bytes | None, strong: bool = False, reduce_mode: int = REDUCE_ALL):
+    """collective: this process becomes rank `rank` of `world` (one process per GPU); world <= 0 switches sharding off"""
+    buf = (C.c_uint8 * 128)(*comm_id) if comm_id else None
+    check(lib().pupil_set_shard(rank, world, buf, int(strong), reduce_mode))
+
+
+def set_shard_plan(strong: bool):
+    check(lib().pupil_set_shard_plan(int(strong)))
+
+
+def synchronize():
+    check(lib().pupil_synchronize())
 
 
 def run(n_pass_runs: int = 1):

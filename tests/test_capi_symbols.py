@@ -18,6 +18,7 @@ def _declared(header: Path, prefix: str):
 def built():
     from pupiloptixlab_b200 import build
     build.build_pb2()
+    build.build_kat()
     build.build_host()
     return build.BUILD
 
@@ -28,6 +29,18 @@ def test_libpb2_exports_header_symbols(built):
     lib = ctypes.CDLL(str(built / "libpb2.so"))
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, missing
+
+
+def test_kat_hooks_live_in_their_own_library(built):
+    """the known-answer hooks are test infrastructure: declared in include/pb2_kat.h, exported by libpb2_kat.so, absent from libpb2.so"""
+    names = _declared(ROOT / "include" / "pb2_kat.h", "pb2_")
+    assert names == ["pb2_kat", "pb2_kat_last_error"]
+    ctypes.CDLL(str(built / "libpb2.so"), mode=ctypes.RTLD_GLOBAL)
+    hooks = ctypes.CDLL(str(built / "libpb2_kat.so"))
+    assert all(hasattr(hooks, n) for n in names)
+    import subprocess
+    exported = subprocess.run(["nm", "-D", "--defined-only", str(built / "libpb2.so")], capture_output=True, text=True).stdout
+    assert "kat" not in exported
 
 
 def test_pb2_python_binding_matches_header(built):

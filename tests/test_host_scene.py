@@ -229,3 +229,61 @@ def test_instance_transform_update_matches_a_fresh_scene(port_lib):
         assert a.weight == b.weight and a.select_probability == b.select_probability and a.area == b.area
         for k in range(3):
             assert list(a.pos[k]) == list(b.pos[k]) and list(a.nrm[k]) == list(b.nrm[k])
+
+
+def _two_light_scene():
+    d = scenes.cornell_box(48, 48, 6)
+    # a second emitting object in FRONT of the ceiling lamp in the object list, plus one behind it
+    d.shapes.insert(0, scenes.Shape("cube", scenes.Xf("srt", scale=(0.1, 0.1, 0.1), translate=(-0.5, 0.3, 0.2)), scenes.Bsdf("diffuse"), emitter=(9.0, 2.0, 1.0), name="glow_cube"))
+    d.shapes.append(scenes.Shape("sphere", scenes.Xf("srt", translate=(0.4, 0.3, 0.3)), scenes.Bsdf("diffuse"), emitter=(1.0, 5.0, 2.0), center=(0, 0, 0), radius=0.1, name="bulb"))
+    return d
+
+
+def test_removing_an_emitting_object_takes_its_emitters_out_of_the_table(port_lib):
+    """World::RemoveRenderObject: the removed object's entries leave EmitterHelper's table, later objects' offsets move down
+    and the selection probabilities are those of a scene that never held the object (world.cpp)"""
+    d = _two_light_scene()
+    pupil.load_scene(d, host_only=True)
+    before = pupil.instances()
+    assert [i["emitter_offset"] for i in before if i["emitter_offset"] >= 0] == [0, 12, 14]
+    pupil.remove_instance(0)
+    fresh = _two_light_scene()
+    del fresh.shapes[0]
+    o = orc.OracleScene(port_lib, fresh)
+    ins = pupil.instances()
+    assert len(ins) == len(fresh.shapes)
+    assert [i["emitter_offset"] for i in ins if i["emitter_offset"] >= 0] == [0, 2]
+    areas, _ = pupil.emitters()
+    oareas = o.area_emitters()
+    assert len(areas) == len(oareas) == 3
+    for a, b in zip(areas, oareas):
+        assert a.type == b.type and a.weight == b.weight and a.select_probability == b.select_probability and a.area == b.area
+        for k in range(3):
+            assert list(a.pos[k]) == list(b.pos[k])
+    # removing the LAST emitter shifts nothing
+    pupil.remove_instance(len(ins) - 1)
+    assert [i["emitter_offset"] for i in pupil.instances() if i["emitter_offset"] >= 0] == [0]
+    assert len(pupil.emitters()[0]) == 2
+    with pytest.raises(pupil.PupilError):
+        pupil.remove_instance(99)
+
+
+def test_hostile_xml_fails_instead_of_crashing():
+    """element nesting is capped (the reader recurses per level), numeric character references decode, a film without
+    pixels falls back to the default size (ADVICE r1, xml.cpp / Scene::LoadXmlObj)"""
+    L = pupil.lib()
+    deep = b"<scene>" + b"<a>" * 200000 + b"</a>" * 200000 + b"</scene>"
+    assert L.pupil_parse_scene_xml_string(deep, None) != 0
+    ok_depth = b"<scene version='3.0.0'>" + b"<x>" * 100 + b"</x>" * 100 + b"<shape type='cube' id='c&#49;&#x32;'/></scene>"
+    assert L.pupil_parse_scene_xml_string(ok_depth, None) == 0
+    assert len(pupil.instances()) == 1
+    bad_film = XML.replace('value="$resx"', 'value="0"').replace('value="$res"', 'value="-5"')
+    pupil.lib().pupil_set_log_level(0)
+    try:
+        assert L.pupil_parse_scene_xml_string(bad_film.encode(), None) == 0
+    finally:
+        pupil.lib().pupil_set_log_level(1)
+    w, h, _ = pupil.film()
+    assert (w, h) == (768, 576)
+    s2c, _, _ = pupil.camera()
+    assert np.isfinite(s2c).all()

@@ -26,6 +26,21 @@ def test_plan_covers_every_seed_once():
         shard.plan(2, 2, 0, 1)
 
 
+def test_strong_plan_splits_a_fixed_job():
+    """pb2_shard_plan, strong: the step's sample count is fixed and split; ragged counts and more ranks than samples included"""
+    from pupiloptixlab_b200 import shard
+    for world in (1, 2, 3, 4, 8):
+        for spp in (1, 5, 8, 64, 1024):
+            seen = []
+            for step in range(2):
+                parts = [shard.plan(r, world, step, spp, strong=True) for r in range(world)]
+                assert all(p.total_spp == spp for p in parts) and sum(p.spp for p in parts) == spp
+                assert max(p.spp for p in parts) - min(p.spp for p in parts) <= 1
+                for p in parts:
+                    seen += p.seeds()
+            assert sorted(seen) == list(range(2 * spp))
+
+
 def _worker(rank, world, port, out_path):
     sys.path[:0] = [str(ROOT), str(ROOT / "tests")]
     import torch

@@ -10,6 +10,7 @@ Rays are resident in HBM; timing = CUDA events around `reps` launches of pb2_tra
 """
 import argparse
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -20,20 +21,8 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-def camera_rays(s2c, c2w, w, h, seed=0):
-    rng = np.random.default_rng(seed)
-    ys, xs = np.meshgrid(np.arange(h, dtype=np.float32), np.arange(w, dtype=np.float32), indexing="ij")
-    u = (xs + rng.random((h, w), dtype=np.float32)) / np.float32(w)
-    v = (ys + rng.random((h, w), dtype=np.float32)) / np.float32(h)
-    pf = np.stack([u, v, np.zeros_like(u), np.ones_like(u)], -1).reshape(-1, 4)
-    d = pf @ s2c.T
-    d = d[:, :3] / d[:, 3:4]
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    dw = d @ c2w[:3, :3].T
-    dw /= np.linalg.norm(dw, axis=1, keepdims=True)
-    rays = np.zeros((w * h, 8), np.float32)
-    rays[:, 0:3], rays[:, 3], rays[:, 4:7], rays[:, 7] = c2w[:3, 3], 1e-3, dw, 1e16
-    return rays
+sys.path.insert(0, str(ROOT / "tools"))
+from ray_batches import bounce_rays, camera_rays, hit_points, measure_trace, shadow_rays  # noqa: E402
 
 
 def main():
@@ -50,6 +39,7 @@ def main():
                     "the 2^21-ray batches of config C4 give each resident warp ~200 rays, so ramp-up and tail are a visible share of the launch")
     ap.add_argument("--l2", type=str, default="", help="comma list of persist_mb:window_mb pairs for the L2 access-policy window over the top of the node array")
     ap.add_argument("--coop", type=int, default=-1, help="warp-cooperative primitive tests: 1 on, 0 off, -1 auto")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity check of 8192 sampled rays per batch against the oracle's CPU BVH")
     args = ap.parse_args()
     import torch
     from pupiloptixlab_b200 import pupil, scenes
@@ -84,42 +74,38 @@ def main():
     s2c, c2w, _ = pupil.camera()
     prim = camera_rays(s2c, c2w, args.width, args.height)
 
-    def trace(rays_np, any_hit, label):
-        n = len(rays_np)
-        rays = torch.from_numpy(rays_np).cuda()
-        tuvp = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
-        inst = torch.zeros(n, dtype=torch.int32, device="cuda")
-        occ = torch.zeros(n, dtype=torch.int32, device="cuda")
-        torch.cuda.synchronize()
+    oracle = None
+    if not args.no_check:  # the oracle is the checker here, never the thing measured (its time is not part of any number printed)
+        sys.path.insert(0, str(ROOT / "tests"))
+        import orc
+        from gpu_util import compare_hits
+        t0 = time.perf_counter()
+        oracle = orc.OracleScene(orc.port(), desc)
+        print(json.dumps({"what": "oracle_bvh", "seconds": time.perf_counter() - t0}), flush=True)
+    check_rng = np.random.default_rng(99)
 
-        def launch():
-            if any_hit:
-                scene.trace_any_dev(rays.data_ptr(), n, occ.data_ptr())
-            else:
-                scene.trace_closest_dev(rays.data_ptr(), n, tuvp.data_ptr(), inst.data_ptr())
-        for _ in range(3):
-            launch()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for _ in range(args.reps):
-                launch()
-            e1.record(stream)
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / args.reps
-        scene.set_option("counting", 1)
-        launch()
-        scene.synchronize()
-        st = scene.render_stats_raw()
-        scene.set_option("counting", 0)
-        nodes, prims = st.nodes_visited, st.prims_tested
-        out_b = 4 if any_hit else 20
-        bytes_ = n * (32 + out_b) + nodes * 80 + prims * 48
-        hits = int((occ != 0).sum().item()) if any_hit else int((inst >= 0).sum().item())
-        print(json.dumps({"what": label, "rays": n, "ms": ms, "mrays_per_s": n / ms / 1e3, "hit_fraction": hits / n, "nodes_per_ray": nodes / n,
-                          "prims_per_ray": prims / n,
-                          "roofline": {"bound": "hbm", "achieved": bytes_ / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                       "frac": bytes_ / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_ray": bytes_ / n}}), flush=True)
+    def check(rays_np, any_hit, tuvp_t, inst_t, occ_t, label):
+        """8192 sampled rays of the batch against the oracle's CPU BVH: ids exact up to ties, t within 1e-5 relative"""
+        sel = check_rng.choice(len(rays_np), min(8192, len(rays_np)), replace=False)
+        sub = rays_np[sel]
+        if any_hit:
+            ref = oracle.trace_any(sub)
+            got = occ_t.cpu().numpy()[sel] != 0
+            bad = int(np.count_nonzero(got != (ref != 0)))
+            assert bad <= 4, f"{label}: {bad} of {len(sel)} any-hit answers differ from the oracle"
+            return {"checked": len(sel), "differ": bad}
+        ref, _ = oracle.trace_closest(sub, threads=os.cpu_count())
+        tu, ins = tuvp_t.cpu().numpy()[sel], inst_t.cpu().numpy()[sel]
+        gpu = np.zeros(len(sel), ref.dtype)
+        gpu["t"], gpu["u"], gpu["v"], gpu["inst"] = tu[:, 0], tu[:, 1], tu[:, 2], ins
+        gpu["prim"] = np.where(ins >= 0, np.ascontiguousarray(tu[:, 3]).view(np.uint32).astype(np.int64), -1)
+        ties = compare_hits(gpu, ref, sub)
+        return {"checked": len(sel), "ties_excused": ties}
+
+    def trace(rays_np, any_hit, label):
+        rec, tuvp, inst, occ = measure_trace(torch, scene, stream, rays_np, any_hit, args.reps, peak, label)
+        rec["parity_vs_oracle_bvh"] = check(rays_np, any_hit, tuvp, inst, occ, label) if oracle is not None else None
+        print(json.dumps(rec), flush=True)
         return tuvp.cpu().numpy(), inst.cpu().numpy()
 
     sweep = [tuple(int(y) for y in x.split(":")) for x in args.refill.split(",")] if args.refill else [None]
@@ -128,19 +114,10 @@ def main():
         scene.set_option("refill_threshold", thr[0])
 
     tuvp, inst = trace(prim, False, "closest_primary_1080p")
-    hit = inst >= 0
-    pos = prim[hit, 0:3] + tuvp[hit, 0:1] * prim[hit, 4:7]
+    pos = hit_points(prim, tuvp[:, 0], inst)
     rng = np.random.default_rng(7)
     k = min(args.rays, len(pos))
-    sel = rng.choice(len(pos), k, replace=len(pos) < k)
-    p = pos[sel]
-    # cosine-distributed directions about +Y (the terrain is a height field)
-    u1, u2 = rng.random(k, dtype=np.float32), rng.random(k, dtype=np.float32)
-    r, phi = np.sqrt(u1), 2 * np.pi * u2
-    d = np.stack([r * np.cos(phi), np.sqrt(np.maximum(0, 1 - u1)), r * np.sin(phi)], -1).astype(np.float32)
-    inco = np.zeros((k, 8), np.float32)
-    inco[:, 0:3], inco[:, 3], inco[:, 4:7], inco[:, 7] = p, 1e-3, d, 1e16
-    inco = inco[rng.permutation(k)]
+    inco, p = bounce_rays(pos, k, rng)
     if args.orders:  # how much of the incoherent batch's cost is ordering: same rays, binned by direction octant / sorted along a Morton curve of the origins
         octant = (inco[:, 4] >= 0) * 4 + (inco[:, 5] >= 0) * 2 + (inco[:, 6] >= 0)
         trace(inco[np.argsort(octant, kind="stable")], False, "closest_incoherent_bounce binned by octant")
@@ -160,11 +137,7 @@ def main():
             apply(thr)
             trace(prim, False, f"closest_primary_1080p thr={thr}")
         trace(inco, False, f"closest_incoherent_bounce thr={thr}")
-    light = np.array([0.0, 12.0, 0.0], np.float32) + rng.uniform(-3, 3, (k, 3)).astype(np.float32) * np.array([1, 0, 1], np.float32)
-    dl = light - p
-    dist = np.linalg.norm(dl, axis=1, keepdims=True)
-    sh = np.zeros((k, 8), np.float32)
-    sh[:, 0:3], sh[:, 3], sh[:, 4:7], sh[:, 7] = p, 1e-4, dl / dist, dist[:, 0] - 1e-4
+    sh = shadow_rays(p, rng)
     for thr in sweep:
         if thr is not None:
             apply(thr)
