@@ -20,8 +20,8 @@ max depth 8.  Numbers:
                ms and the three traversal batches (Mrays/s, roofline fraction, nodes / primitives per ray); c5: the 4K
                1024-spp job on this many GPUs (strong scaling: the job is fixed, the ranks split its sample indices)
 N > 1: one process per GPU inside the product (PTPass::SetShard -> pb2_shard_plan / pb2_comm_reduce_frames, NCCL loaded by
-libpb2.so): rank r renders seeds base + r + k N into plain sums; the reduction (reduce-scatter + finalize + all-gather, or
-reduce to rank 0 with --reduce root) runs on its own stream and overlaps the next step's render up to its first accumulate
+libpb2.so): rank r renders seeds base + r + k N into plain sums; the reduction (ncclReduce to rank 0 + finalize, or
+reduce-scatter + finalize + all-gather with --reduce all) runs on its own stream and overlaps the next step's render up to its first accumulate
 kernel.  --scaling weak (default): every rank renders the step's sample count; --scaling strong: the ranks split it.
 torch.distributed carries the NCCL id to the ranks and the max-over-ranks of the timings; it is not on the data path.
 """
@@ -362,8 +362,9 @@ def main():
     ap.add_argument("--terrain-n", type=int, default=3873, help="terrain grid size n (2*n*n triangles; 3873 -> 30.0 M)")
     ap.add_argument("--cpu-spp", type=int, default=2, help="spp of the CPU sample per step / for the cpu_baseline leg")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="N > 1: every rank renders the step's spp (weak) or the ranks split it (strong)")
-    ap.add_argument("--reduce", default="all", choices=["all", "root"], help="N > 1: reduce-scatter + finalize + all-gather, or reduce to rank 0")
-    ap.add_argument("--builder", type=int, default=0, help="BVH builder of the c4 record (pb2_scene_set_builder)")
+    ap.add_argument("--reduce", default="root", choices=["all", "root"],
+                    help="N > 1: reduce to rank 0 + finalize (default: measured faster, profiles/README.md), or reduce-scatter + finalize + all-gather")
+    ap.add_argument("--builder", type=int, default=0, help="BVH builder (pb2_scene_set_builder): 0 LBVH, 2 SAH-driven clustering")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the c3 / c4 / c5 sub-records")
@@ -385,10 +386,13 @@ def main():
     torch.cuda.set_device(local)
     dist = None
     pupil.init(local, log_level=1)
+    if args.builder:
+        pupil.set_bvh_builder(args.builder)  # sticky: every scene of this run is built with it
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout for the one JSON line
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
         box = [pupil.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)  # plumbing: the 128-byte NCCL id of the product's own communicator
         pupil.set_shard(rank, world, box[0], strong=args.scaling == "strong", reduce_mode=pupil.REDUCE_ALL if args.reduce == "all" else pupil.REDUCE_ROOT)
@@ -464,8 +468,10 @@ def main():
     roofline = None
     if rank == 0:
         scene.set_option("counting", 1)
-        step(warmup)
-        cs = pupil.render_stats()
+    step(warmup)  # on EVERY rank: a sharded step ends in a collective (pb2_comm_reduce_frames); only rank 0 counts
+    cs = pupil.render_stats()
+    pupil.synchronize()
+    if rank == 0:
         scene.set_option("counting", 0)
         spp_rank = cs.closest_rays and (spp if not strong else max(1, -(-spp // world)))  # frames this rank rendered in the counting pass
         per_step, bvh_cached, nodes_c, prims_c = stage_bytes(cs, build, desc, n_px, spp_rank, n_ext / args.steps, n_shadow / args.steps)

@@ -184,10 +184,11 @@ int pb2_scene_set_camera(pb2_scene *scene, const float sample_to_camera[16], con
 /* replaces GAS::Create + IAS::Create (framework/world/gas_manager.cpp:69-245, ias_manager.cpp:29-114):
  * GPU build of one world-space compressed 8-wide BVH over every instance.  stats may be NULL. */
 int pb2_bvh_build(pb2_scene *scene, pb2_build_stats *stats);
-/* builder: 0 = LBVH over 63-bit Morton codes (default), 1 = binned-SAH sweep along the Morton order (16 equal-count bins
- * per node, exact sweep below 17 primitives; bvh_sah.cu).  On the 30 M-triangle terrain builder 1 is measured WORSE
- * (40 vs 24 nodes per primary ray, 85 vs 25 ms build, profiles/README.md): splits that do not fall on octree-cell
- * boundaries of the Z-curve produce overlapping boxes.  A spatial (re-partitioning) binned SAH is not built yet. */
+/* builder: 0 = LBVH over 63-bit Morton codes; 1 = binned-SAH sweep along the Morton order (16 equal-count bins per node, exact
+ * sweep below 17 primitives; bvh_sah.cu — measured worse than LBVH: splits that do not fall on octree-cell boundaries of the
+ * Z-curve produce overlapping boxes); 2 = SAH-driven bottom-up clustering (bvh_ploc.cu): mutual nearest neighbours by the
+ * surface area of their union, searched `ploc_radius` clusters to either side along the Morton curve — the fast-trace build
+ * the reference asks OptiX for (OPTIX_BUILD_FLAG_PREFER_FAST_TRACE, gas_manager.cpp:191).  Measured numbers: DESIGN.md 8. */
 int pb2_scene_set_builder(pb2_scene *scene, int builder);
 
 /* parity / benchmark hooks for the two optixTrace flavours (main.cu:80-85,161-166; emitter.h:91-100).
@@ -213,7 +214,8 @@ int pb2_render_stats_get(pb2_scene *scene, pb2_render_stats *stats); /* synchron
  * material type; default -1), refill_threshold (persistent traversal), shade_variant (4 | 6 | 7 | 8 resident CTAs per SM),
  * two_lanes (two batches in flight on two streams), coop_prims (warp-cooperative primitive tests: 1 on, 0 off, -1 = auto
  * by scene size), l2_persist_mb / l2_window_mb (persisting-L2 access-policy window over the top levels of the node array;
- * 0 = off, the default).  Unknown names fail with PB2_ERR_ARG. */
+ * 0 = off, the default), ploc_radius (builder 2: neighbours searched on either side, 1..16, default 8).  Unknown names fail
+ * with PB2_ERR_ARG. */
 int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value);
 /* frame[i] = (sum[i].xyz / total_spp, 1) on the scene's stream: the last step of a sharded render whose sums were combined
  * by the caller's own collective (pb2_comm_reduce_frames below does both).   */

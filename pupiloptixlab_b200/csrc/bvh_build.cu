@@ -227,22 +227,32 @@ struct CollapseCtx {
 struct Ref {
     float3 lo, hi;
     int ref;   // >= 0 internal binary node, < 0 leaf (~sorted position)
-    int first; // first sorted primitive position
-    int count;
+    int count; // primitives below (range.y of an internal node: the only field of `range` the collapse reads — the clustering
+               // builder's subtrees are not contiguous ranges of the sorted order)
 };
 __device__ __forceinline__ Ref load_ref(const CollapseCtx &c, int ref) {
     Ref r;
     r.ref = ref;
     if (ref >= 0) {
         r.lo = mk3(c.t.lo[ref]), r.hi = mk3(c.t.hi[ref]);
-        const int2 rg = c.t.range[ref];
-        r.first = rg.x, r.count = rg.y;
+        r.count = c.t.range[ref].y;
     } else {
         const uint32_t p = c.sorted[~ref];
         r.lo = mk3(c.box_lo[p]), r.hi = mk3(c.box_hi[p]);
-        r.first = ~ref, r.count = 1;
+        r.count = 1;
     }
     return r;
+}
+// sorted positions of the (at most kLeafMax) primitives below a small subtree, left to right
+__device__ __forceinline__ int collect_leaves(const CollapseCtx &c, int ref, int *out) {
+    int stack[kLeafMax + 1], sp = 0, n = 0;
+    stack[sp++] = ref;
+    while (sp > 0 && n < kLeafMax) {
+        const int r = stack[--sp];
+        if (r < 0) out[n++] = ~r;
+        else stack[sp++] = c.t.right[r], stack[sp++] = c.t.left[r];
+    }
+    return n;
 }
 // primitive records into BVH leaf order: prims_out[dst_of_sorted[i]] = prims_in[sorted[i]]
 __global__ void __launch_bounds__(256) k_scatter_prims(const PrimRec *__restrict__ prims_in, const uint32_t *__restrict__ sorted,
@@ -401,7 +411,9 @@ __global__ void __launch_bounds__(128, PB2_COLLAPSE_MINB) k_collapse(CollapseCtx
             meta[s] = (unary << 5) | prim_off;
             // the 48-byte records are moved by k_scatter_prims afterwards (one thread per record instead of a dependent
             // gather loop per wide node: the loop was the kernel's largest single stall)
-            for (int k = 0; k < r.count; ++k) c.dst_of_sorted[r.first + k] = prim_base + prim_off + k;
+            int pos[kLeafMax];
+            const int found = collect_leaves(c, r.ref, pos);
+            for (int k = 0; k < found; ++k) c.dst_of_sorted[pos[k]] = prim_base + prim_off + k;
             prim_off += r.count;
             sah_local += half_area(r.lo, r.hi) * r.count;
         }
@@ -425,6 +437,9 @@ __global__ void __launch_bounds__(128, PB2_COLLAPSE_MINB) k_collapse(CollapseCtx
 }
 }// namespace
 
+// bvh_ploc.cu: SAH-driven bottom-up clustering producing the same BinTree arrays; returns the root's node index
+int build_binary_ploc(cudaStream_t st, uint32_t n, const float4 *box_lo, const float4 *box_hi, const uint32_t *sorted, int *left, int *right, int2 *range,
+                      float4 *lo, float4 *hi, int radius, uint32_t *rounds_out);
 // bvh_sah.cu: binned-SAH binary tree producing the same BinTree arrays + `sorted` permutation
 bool sah_builder_available();
 void build_binary_sah(cudaStream_t st, uint32_t n, const float4 *box_lo, const float4 *box_hi, const uint32_t *sorted, int *left, int *right, int2 *range,
@@ -499,6 +514,7 @@ void build_bvh(Scene &s) {
     DevBuf<int2> range(n);
     DevBuf<float4> nlo(n), nhi(n);
     BinTree t{ left.ptr, right.ptr, parent.ptr, range.ptr, nlo.ptr, nhi.ptr, n };
+    int root_ref = 0; // binary node the collapse starts from (node 0 for the top-down builders)
 
     {
         DevBuf<uint64_t> keys(n), keys_sorted(n);
@@ -509,7 +525,10 @@ void build_bvh(Scene &s) {
         PB2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.ptr, keys_sorted.ptr, vals.ptr, sorted.ptr, (int)n, 0, 63, st));
         DevBuf<uint8_t> tmp(tmp_bytes);
         PB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys.ptr, keys_sorted.ptr, vals.ptr, sorted.ptr, (int)n, 0, 63, st));
-        if (n > 1 && s.builder == 1 && sah_builder_available()) {
+        if (n > 1 && s.builder == 2) {
+            // bottom-up clustering by the surface area of the union (bvh_ploc.cu); node boxes come out of the merges
+            root_ref = build_binary_ploc(st, n, box_lo.ptr, box_hi.ptr, sorted.ptr, left.ptr, right.ptr, range.ptr, nlo.ptr, nhi.ptr, s.ploc_radius, nullptr);
+        } else if (n > 1 && s.builder == 1 && sah_builder_available()) {
             // binned SAH over the Morton-ordered sequence (bvh_sah.cu); node boxes come out of the sweep
             build_binary_sah(st, n, box_lo.ptr, box_hi.ptr, sorted.ptr, left.ptr, right.ptr, range.ptr, nlo.ptr, nhi.ptr);
         } else if (n > 1) {
@@ -532,7 +551,7 @@ void build_bvh(Scene &s) {
     uint32_t init_counters[4] = { 1, 0, 0, 0 };
     PB2_CUDA(cudaMemcpyAsync(counters.ptr, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, st));
     DevBuf<uint4> qa(n), qb(n);
-    uint4 root = make_uint4(0u, n > 1 ? 0u : (uint32_t)~0, 0u, 0u); // n == 1: leaf ref ~0
+    uint4 root = make_uint4(0u, n > 1 ? (uint32_t)root_ref : (uint32_t)~0, 0u, 0u); // n == 1: leaf ref ~0
     PB2_CUDA(cudaMemcpyAsync(qa.ptr, &root, sizeof root, cudaMemcpyHostToDevice, st));
     DevBuf<uint32_t> dst_of_sorted(n);
     CollapseCtx cc{ t, sorted.ptr, box_lo.ptr, box_hi.ptr, prims_in.ptr, dst_of_sorted.ptr, nodes.ptr, counters.ptr, sah.ptr };

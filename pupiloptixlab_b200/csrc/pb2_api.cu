@@ -489,7 +489,7 @@ int pb2_scene_set_camera(pb2_scene *scene, const float s2c[16], const float c2w[
     PB2_CATCH
 }
 int pb2_scene_set_builder(pb2_scene *scene, int builder) {
-    if (!scene || builder < 0 || builder > 1) return fail(PB2_ERR_ARG, "pb2_scene_set_builder: 0 = LBVH, 1 = binned SAH along the Morton order");
+    if (!scene || builder < 0 || builder > 2) return fail(PB2_ERR_ARG, "pb2_scene_set_builder: 0 = LBVH, 1 = binned SAH along the Morton order, 2 = SAH-driven clustering");
     S(scene)->builder = builder;
     S(scene)->bvh_valid = false;
     return PB2_OK;
@@ -597,6 +597,7 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     else if (n == "two_lanes") s.two_lanes = value != 0;
     else if (n == "coop_prims") s.coop_prims = (int)std::min<int64_t>(1, std::max<int64_t>(-1, value));
     else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);
+    else if (n == "ploc_radius") s.ploc_radius = (int)std::min<int64_t>(16, std::max<int64_t>(1, value)), s.bvh_valid = false;
     else if (n == "l2_persist_mb") s.l2_persist_mb = (int)std::min<int64_t>(1024, std::max<int64_t>(0, value)), s.l2_dirty = true;
     else if (n == "l2_window_mb") s.l2_window_mb = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value)), s.l2_dirty = true;
     else return fail(PB2_ERR_ARG, "pb2_scene_set_option: unknown option " + n);

@@ -37,7 +37,8 @@ struct Scene {
     DevBuf<uint32_t> trace_work; // work counter of the persistent trace kernels
     uint32_t n_nodes = 0, n_prims = 0;
     bool bvh_valid = false;
-    int builder = 0; // 0 LBVH (default: measured better on every config so far), 1 binned SAH sweep along the Morton order
+    int builder = 0; // 0 LBVH, 1 binned SAH sweep along the Morton order, 2 SAH-driven bottom-up clustering (bvh_ploc.cu)
+    int ploc_radius = 8; // neighbours searched on either side along the Morton curve (builder 2)
     pb2_build_stats build_stats{};
 
     // options

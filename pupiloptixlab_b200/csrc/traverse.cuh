@@ -19,6 +19,9 @@ namespace pb2 {
 #ifndef PB2_APPROX_IDIR
 #define PB2_APPROX_IDIR 1
 #endif
+#ifndef PB2_TRACE_PIPE
+#define PB2_TRACE_PIPE 0
+#endif
 #ifndef PB2_STACK_SIZE
 #define PB2_STACK_SIZE 32
 #endif
@@ -180,7 +183,12 @@ struct TravStack {
         return sp < kSmemStack ? sm[sp * 128] : lo[sp - kSmemStack];
     }
 };
-PB2_D void node_step(const SceneView &sv, RayState &r, const TravStack &stack) {
+struct NodeWords { // the five 128-bit words of a wide node, in registers between the fetch and the test
+    float4 n0;
+    uint4 n1, n2, n3, n4;
+};
+// pops the nearest pending internal node of the ray and requests its five words; the siblings that remain go (back) to the stack
+PB2_D void node_pop_fetch(const SceneView &sv, RayState &r, const TravStack &stack, NodeWords &w) {
     if (!(r.G.y & 0xff000000u)) r.G = stack.pop(r.sp);
     const uint32_t bit = 31u - __clz(r.G.y);
     r.G.y &= ~(1u << bit);
@@ -188,9 +196,13 @@ PB2_D void node_step(const SceneView &sv, RayState &r, const TravStack &stack) {
     const uint32_t rel = __popc(r.G.y & 0xffu & ((1u << slot) - 1u));
     const Bvh8Node *np = sv.nodes + (r.G.x + rel);
     if (r.G.y & 0xff000000u) stack.push(r.sp, r.G);
-
-    const float4 n0 = __ldg(&np->n0);
-    const uint4 n1 = __ldg(&np->n1), n2 = __ldg(&np->n2), n3 = __ldg(&np->n3), n4 = __ldg(&np->n4);
+    w.n0 = __ldg(&np->n0);
+    w.n1 = __ldg(&np->n1), w.n2 = __ldg(&np->n2), w.n3 = __ldg(&np->n3), w.n4 = __ldg(&np->n4);
+}
+// tests the eight children of a fetched node, leaves the hit children in G / T
+PB2_D void node_test(RayState &r, const NodeWords &w) {
+    const float4 n0 = w.n0;
+    const uint4 n1 = w.n1, n2 = w.n2, n3 = w.n3, n4 = w.n4;
     const bool px = r.idir.x >= 0.f, py = r.idir.y >= 0.f, pz = r.idir.z >= 0.f;
     const uint32_t oct4 = r.oct * 0x01010101u;
     const uint32_t ebits = __float_as_uint(n0.w);
@@ -227,6 +239,11 @@ PB2_D void node_step(const SceneView &sv, RayState &r, const TravStack &stack) {
     r.T = hitmask & 0x00ffffffu;
     r.prim_base = n1.y;
 }
+PB2_D void node_step(const SceneView &sv, RayState &r, const TravStack &stack) {
+    NodeWords w;
+    node_pop_fetch(sv, r, stack, w);
+    node_test(r, w);
+}
 
 // resident 128-thread CTAs per SM the trace kernels are compiled for: 9 (56 registers) with the per-lane primitive loop,
 // 8 (64 registers) with the warp-cooperative one
@@ -251,8 +268,136 @@ struct CoopShared {                // per warp
 // (profiles/README.md): +7 % / +10 % Mrays/s for incoherent closest-hit / any-hit rays on the 30 M-triangle terrain, where
 // few lanes reach a leaf per step; -17 % on the 36-triangle Cornell box, where every lane does and the bookkeeping only
 // adds instructions.  The host picks per scene (Scene::coop_prims).
+// Pipelined form of the cooperative loop below.  ncu (30 M-triangle terrain, incoherent rays, profiles/r2b_c4_ncu.md): 41 % of
+// the stall samples wait on the long scoreboard, in two places per iteration — the first use of the node words and the first
+// use of the primitive words — one after the other.  Here the NEXT node of every lane is popped and requested right after the
+// current node's test, before the primitive phase: its latency passes behind the primitive fetch and tests, and the warp waits
+// once per iteration instead of twice.  The node words live in registers across the primitive phase (more registers per thread:
+// PB2_TRACE_MINB_PIPE resident CTAs).  Same node and primitive tests in the same order per ray; a ray's primitives are still
+// tested before its next node (hit.t is current when the prefetched node is tested).
+template<bool ANY, bool COUNT, bool TRIS, class IO>
+PB2_D void trace_persistent_pipe(const SceneView &sv, IO &io, uint32_t *__restrict__ work_counter, TraceCounters *ctr, int refill_threshold) {
+    constexpr uint32_t kFull = 0xffffffffu;
+    __shared__ CoopShared s_coop[kTraceWarps];
+    CoopShared &sm = s_coop[threadIdx.x >> 5];
+    const uint32_t n = io.size();
+    const uint32_t lane = threadIdx.x & 31u;
+    __shared__ uint2 s_stack[(kSmemStack > 0 ? kSmemStack : 1) * 128];
+    uint2 stack_local[PB2_STACK_SIZE - kSmemStack];
+    const TravStack stack{ s_stack + threadIdx.x, stack_local };
+    RayState r;
+    NodeWords w;
+    r.T = 0u, r.G = make_uint2(0u, 0u), r.sp = 0;
+    uint32_t ray = 0;
+    bool busy = false, fetched = false; // fetched: w holds a node of this lane's ray that has not been tested yet
+    bool exhausted = false;
+    for (;;) {
+        const uint32_t busy_mask = __ballot_sync(kFull, busy);
+        if (!exhausted && __popc(busy_mask) < refill_threshold) {
+            const uint32_t idle = ~busy_mask;
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
+            base = __shfl_sync(kFull, base, 0);
+            const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
+            if (!busy && mine < n) {
+                float3 o, d;
+                float tmin, tmax;
+                ray = io.load(mine, o, d, tmin, tmax);
+                ray_begin(r, o, d, tmin, tmax, sv.n_nodes == 0);
+                busy = true;
+                if (ray_has_nodes(r)) { // the root: nothing to hide this fetch behind
+                    node_pop_fetch(sv, r, stack, w);
+                    r.G.y &= 0x00ffffffu;
+                    fetched = true;
+                }
+            }
+            exhausted = base + __popc(idle) >= n;
+        } else if (busy_mask == 0u) {
+            break;
+        }
+        // ---- test the node requested one iteration ago, then request the next one ----
+        if (fetched) {
+            node_test(r, w);
+            fetched = false;
+            if (COUNT) ++ctr->nodes;
+        }
+        if (busy && ray_has_nodes(r)) {
+            // the group left by the test stays in r.G for the NEXT pop; node_pop_fetch consumes one node of it and pushes the rest
+            node_pop_fetch(sv, r, stack, w);
+            r.G.y &= 0x00ffffffu; // what remains of the group is on the stack now
+            fetched = true;
+        }
+        // ---- primitives of the node just tested, warp-cooperatively (as in trace_persistent) ----
+        for (;;) {
+            const uint32_t T = busy ? r.T : 0u;
+            if (!__any_sync(kFull, T != 0u)) break;
+            const uint32_t cnt = min((uint32_t)__popc(T), (uint32_t)kPairsPerLane);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                const uint32_t up = __shfl_up_sync(kFull, incl, dlt);
+                if ((int)lane >= dlt) incl += up;
+            }
+            const uint32_t total = __shfl_sync(kFull, incl, 31), excl = incl - cnt;
+            sm.o[lane] = make_float4(r.o.x, r.o.y, r.o.z, r.tmin);
+            sm.d[lane] = make_float4(r.d.x, r.d.y, r.d.z, r.hit.t);
+            sm.base[lane] = r.prim_base;
+            sm.best[lane] = ~0ull;
+            {
+                uint32_t tt = T;
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    const uint32_t b = __ffs(tt) - 1;
+                    tt &= tt - 1;
+                    sm.pairs[excl + j] = (uint16_t)((lane << 5) | b);
+                }
+                if (busy) r.T = tt;
+            }
+            __syncwarp();
+            for (uint32_t c = 0; c < total; c += 32u) {
+                const uint32_t k = c + lane;
+                RayHit h;
+                h.t = 0.f, h.u = 0.f, h.v = 0.f, h.prim_slot = 0xffffffffu;
+                if (k < total) {
+                    const uint32_t e = sm.pairs[k], own = e >> 5;
+                    if (!ANY || sm.best[own] == ~0ull) {
+                        const float4 ro = sm.o[own], rd = sm.d[own];
+                        h.t = rd.w;
+                        if (COUNT) ++ctr->prims;
+                        if (intersect_prim<true, TRIS>(sv, sm.base[own] + (e & 31u), mk3(ro), mk3(rd), ro.w, h))
+                            atomicMin(&sm.best[own], ((unsigned long long)__float_as_uint(h.t) << 32) | k);
+                    }
+                }
+                __syncwarp();
+                const unsigned long long b = sm.best[lane];
+                const uint32_t bk = (uint32_t)b;
+                const bool won = busy && b != ~0ull && bk >= c && bk < c + 32u;
+                const uint32_t src = won ? bk - c : lane;
+                const float wt = __shfl_sync(kFull, h.t, src), wu = __shfl_sync(kFull, h.u, src), wv = __shfl_sync(kFull, h.v, src);
+                const uint32_t ws = __shfl_sync(kFull, h.prim_slot, src);
+                if (won) {
+                    r.hit.t = wt, r.hit.u = wu, r.hit.v = wv, r.hit.prim_slot = ws;
+                    if (ANY) r.T = 0u, r.G.y = 0u, r.sp = 0, fetched = false; // occluded: the prefetched node is dropped
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        const bool done = busy && !fetched && !ray_has_nodes(r);
+        if (__any_sync(kFull, done)) {
+            io.commit(done, ray, r.hit, r.hit.prim_slot != 0xffffffffu);
+            if (done) busy = false;
+        }
+    }
+}
+
 template<bool ANY, bool COUNT, bool COOP, bool TRIS, class IO>
 PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ work_counter, TraceCounters *ctr, int refill_threshold = PB2_REFILL_THRESHOLD) {
+#if PB2_TRACE_PIPE
+    if (COOP) {
+        trace_persistent_pipe<ANY, COUNT, TRIS>(sv, io, work_counter, ctr, refill_threshold);
+        return;
+    }
+#endif
     constexpr uint32_t kFull = 0xffffffffu;
     __shared__ CoopShared s_coop[COOP ? kTraceWarps : 1];
     CoopShared &sm = s_coop[COOP ? threadIdx.x >> 5 : 0];

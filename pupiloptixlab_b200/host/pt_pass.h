@@ -70,7 +70,7 @@ private:
     bool m_accumulated_flag = true, m_sum_mode = false;
     unsigned int m_frames_per_run = 1, m_first_seed = 0, m_seed_stride = 1;
     pb2_comm *m_comm = nullptr; // not owned
-    int m_rank = 0, m_n_ranks = 1, m_reduce_mode = PB2_REDUCE_ALL;
+    int m_rank = 0, m_n_ranks = 1, m_reduce_mode = PB2_REDUCE_ROOT;
     bool m_strong = false;
     unsigned int m_shard_step = 0, m_shard_total_spp = 0; // OnRun calls and samples of all ranks since the last restart
 };

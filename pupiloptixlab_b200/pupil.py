@@ -178,7 +178,7 @@ def comm_unique_id() -> bytes:
     return bytes(buf)
 
 
-def set_shard(rank: int, world: int, comm_id: bytes | None, strong: bool = False, reduce_mode: int = REDUCE_ALL):
+def set_shard(rank: int, world: int, comm_id: bytes | None, strong: bool = False, reduce_mode: int = REDUCE_ROOT):
     """collective: this process becomes rank `rank` of `world` (one process per GPU); world <= 0 switches sharding off"""
     buf = (C.c_uint8 * 128)(*comm_id) if comm_id else None
     check(lib().pupil_set_shard(rank, world, buf, int(strong), reduce_mode))

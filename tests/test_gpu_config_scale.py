@@ -159,6 +159,14 @@ def test_degenerate_slivers_and_transformed_spheres_at_scale(port_lib):
     st = s.build()
     assert st.n_prims == n_tris + 64 and st.n_spheres == 64
     rays = random_rays(65536, 77, extent=34.0)
+    # a quarter of the rays aimed at the spheres (random targets rarely find 64 small spheres among 2 M triangles)
+    centres = np.stack([osc.instance_xform(1 + k)[:3, 3] for k in range(64)])
+    aim = np.arange(0, len(rays), 4)
+    tgt = centres[rng.integers(0, 64, len(aim))] + rng.normal(scale=0.4, size=(len(aim), 3))
+    away = rng.normal(size=(len(aim), 3))
+    rays[aim, 0:3] = (tgt + 4.0 * away / np.linalg.norm(away, axis=1, keepdims=True)).astype(np.float32)  # start close: the soup is dense
+    d = tgt - rays[aim, 0:3]
+    rays[aim, 4:7] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
     gpu = s.trace_closest(rays)
     sel = np.random.default_rng(3).choice(len(rays), 8192, replace=False)
     ref, _ = osc.trace_closest(rays[sel], threads=os.cpu_count())

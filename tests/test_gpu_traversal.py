@@ -24,7 +24,8 @@ def _soup_desc(n_tris, seed, n_spheres=0):
     return scenes.SceneDesc(shapes=shapes)
 
 
-@pytest.mark.parametrize("n_tris,n_spheres,builder", [(1, 0, 0), (2, 0, 0), (3, 1, 0), (4, 0, 0), (37, 3, 0), (1000, 5, 0), (20000, 16, 0), (20000, 16, 1)])
+@pytest.mark.parametrize("n_tris,n_spheres,builder", [(1, 0, 0), (2, 0, 0), (3, 1, 0), (4, 0, 0), (37, 3, 0), (1000, 5, 0), (20000, 16, 0), (20000, 16, 1),
+                                                      (1, 0, 2), (2, 0, 2), (3, 1, 2), (37, 3, 2), (1000, 5, 2), (20000, 16, 2)])
 def test_closest_hit_matches_brute_force(port_lib, n_tris, n_spheres, builder):
     desc = _soup_desc(n_tris, 7 + n_tris, n_spheres)
     osc = orc.OracleScene(port_lib, desc)

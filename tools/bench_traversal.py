@@ -39,6 +39,7 @@ def main():
                     "the 2^21-ray batches of config C4 give each resident warp ~200 rays, so ramp-up and tail are a visible share of the launch")
     ap.add_argument("--l2", type=str, default="", help="comma list of persist_mb:window_mb pairs for the L2 access-policy window over the top of the node array")
     ap.add_argument("--coop", type=int, default=-1, help="warp-cooperative primitive tests: 1 on, 0 off, -1 auto")
+    ap.add_argument("--ploc-radius", type=int, default=0, help="builder 2: neighbours searched on either side along the Morton curve")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check of 8192 sampled rays per batch against the oracle's CPU BVH")
     args = ap.parse_args()
     import torch
@@ -57,10 +58,13 @@ def main():
     t_load = time.perf_counter() - t0
     bs = pupil.build_stats()
     builds = [bs.build_ms]
+    if args.ploc_radius:
+        pupil.scene_handle().set_option("ploc_radius", args.ploc_radius)
     for _ in range(2):  # rebuild twice more: steady-state build time (allocator warm)
         pupil.set_bvh_builder(args.builder if args.builder >= 0 else 0)
         builds.append(pupil.build_stats().build_ms)
     scene = pupil.scene_handle()
+    bs = pupil.build_stats()
     tri_bytes = bs.n_triangles * 230
     print(json.dumps({"what": "bvh_build", "n_prims": bs.n_prims, "n_nodes": bs.n_nodes, "bvh_bytes": bs.bvh_bytes, "build_ms": min(builds),
                       "build_ms_all": builds, "mtris_per_s": bs.n_triangles / min(builds) / 1e3, "sah_cost": bs.sah_cost, "depth": bs.max_depth,
