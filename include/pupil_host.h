@@ -34,6 +34,13 @@ int pupil_parse_scene_xml_string(const char *xml, const char *root_dir);
  * (ShapeManager::LoadMeshShape without the text round trip; arrays are copied; nrm / uv may be NULL) */
 int pupil_register_mesh(const char *key, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t n_vertices,
                         uint32_t n_triangles);
+/* the same without the copy: the caller keeps the four arrays alive (and unchanged) until pupil_unregister_mesh(key) or
+ * pupil_clear_shapes.  Copying a 30 M-triangle mesh (840 MB) was 80 % of the host side of a scene reload; arrays in pinned
+ * memory (cudaHostAlloc / cudaHostRegister) additionally make the upload a straight DMA. */
+int pupil_register_mesh_borrowed(const char *key, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t n_vertices,
+                                 uint32_t n_triangles);
+/* forget one registered mesh; no loaded scene may still use it */
+int pupil_unregister_mesh(const char *key);
 /* forget every cached shape (ShapeManager::Clear) */
 int pupil_clear_shapes(void);
 

@@ -84,6 +84,16 @@ int pupil_register_mesh(const char *key, const float *pos, const float *nrm, con
     if (!util::Singleton<resource::ShapeManager>::instance()->LoadMeshShape(key, pos, nrm, uv, idx, nv, nf)) return Fail("empty mesh");
     return 0;
 }
+int pupil_register_mesh_borrowed(const char *key, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t nv, uint32_t nf) {
+    if (!key || std::strncmp(key, "mem:", 4) != 0) return Fail("mesh keys must start with \"mem:\"");
+    if (!util::Singleton<resource::ShapeManager>::instance()->LoadMeshShape(key, pos, nrm, uv, idx, nv, nf, /*borrow=*/true)) return Fail("empty mesh");
+    return 0;
+}
+int pupil_unregister_mesh(const char *key) {
+    if (!key) return Fail("null key");
+    util::Singleton<resource::ShapeManager>::instance()->DropMeshShape(key);
+    return 0;
+}
 int pupil_register_image(const char *key, const float *rgba, uint32_t width, uint32_t height) {
     if (!key || std::strncmp(key, "mem:", 4) != 0) return Fail("image keys must start with \"mem:\"");
     optix::material::ClearDeviceBitmaps(); // a replaced image may reuse the address a cached texture object was made from

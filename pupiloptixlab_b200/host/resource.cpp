@@ -1,4 +1,6 @@
 #include "resource.h"
+#include <cfloat>
+#include <thread>
 #include "image.h"
 
 #include <charconv>
@@ -363,6 +365,25 @@ bool ReadObj(const std::string &path, std::vector<float> &P, std::vector<float> 
 }
 }// namespace
 
+// bounding box of n packed float3 points, on up to eight threads (15 M vertices: 180 MB to read)
+static util::AABB BoundsOf(const float *pos, uint32_t n) {
+    const unsigned workers = n < (1u << 20) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<util::AABB> part(workers);
+    auto run = [&](unsigned w) {
+        const size_t b = (size_t)n * w / workers, e = (size_t)n * (w + 1) / workers;
+        float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+        for (size_t i = b; i < e; ++i)
+            for (int k = 0; k < 3; ++k) lo[k] = std::min(lo[k], pos[i * 3 + k]), hi[k] = std::max(hi[k], pos[i * 3 + k]);
+        if (e > b) part[w].Merge(util::Float3{ lo[0], lo[1], lo[2] }), part[w].Merge(util::Float3{ hi[0], hi[1], hi[2] });
+    };
+    std::vector<std::thread> threads;
+    for (unsigned w = 1; w < workers; ++w) threads.emplace_back(run, w);
+    run(0);
+    for (auto &t : threads) t.join();
+    util::AABB out;
+    for (auto &p : part) out.Merge(p);
+    return out;
+}
 Shape *ShapeManager::Register(std::unique_ptr<Shape> shape) {
     shape->id = m_shape_id_cnt++;
     Shape *p = shape.get();
@@ -372,11 +393,8 @@ Shape *ShapeManager::Register(std::unique_ptr<Shape> shape) {
 Shape *ShapeManager::MakeMeshShape(std::string_view key, EShapeType type, const MeshData &d) {
     auto shape = std::make_unique<Shape>();
     shape->file_path = key, shape->type = type;
-    shape->mesh.vertex_num = (uint32_t)(d.positions.size() / 3), shape->mesh.face_num = (uint32_t)(d.indices.size() / 3);
-    shape->mesh.positions = d.positions.data();
-    shape->mesh.normals = d.normals.empty() ? nullptr : d.normals.data();
-    shape->mesh.texcoords = d.texcoords.empty() ? nullptr : d.texcoords.data();
-    shape->mesh.indices = d.indices.data();
+    shape->mesh.vertex_num = d.nv, shape->mesh.face_num = d.nf;
+    shape->mesh.positions = d.pos, shape->mesh.normals = d.nrm, shape->mesh.texcoords = d.uv, shape->mesh.indices = d.idx;
     shape->aabb = d.aabb;
     return Register(std::move(shape));
 }
@@ -388,24 +406,43 @@ Shape *ShapeManager::LoadMeshShape(std::string_view file_path) noexcept {
         Log::Warn("mesh load from %s failed", key.c_str());
         return nullptr;
     }
-    for (size_t i = 0; i + 2 < data->positions.size(); i += 3) data->aabb.Merge(util::Float3{ data->positions[i], data->positions[i + 1], data->positions[i + 2] });
+    data->pos = data->positions.data(), data->nrm = data->normals.empty() ? nullptr : data->normals.data();
+    data->uv = data->texcoords.empty() ? nullptr : data->texcoords.data(), data->idx = data->indices.data();
+    data->nv = (uint32_t)(data->positions.size() / 3), data->nf = (uint32_t)(data->indices.size() / 3);
+    data->aabb = BoundsOf(data->pos, data->nv);
     Shape *s = MakeMeshShape(key, EShapeType::_obj, *data);
     m_meshes[key] = std::move(data), m_mesh_shape[key] = s;
     return s;
 }
-Shape *ShapeManager::LoadMeshShape(std::string_view key_, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t nv, uint32_t nf) noexcept {
+Shape *ShapeManager::LoadMeshShape(std::string_view key_, const float *pos, const float *nrm, const float *uv, const uint32_t *idx, uint32_t nv, uint32_t nf,
+                                   bool borrow) noexcept {
     const std::string key(key_);
     if (auto it = m_mesh_shape.find(key); it != m_mesh_shape.end()) return it->second;
     if (!pos || !idx || !nv || !nf) return nullptr;
     auto data = std::make_unique<MeshData>();
-    data->positions.assign(pos, pos + (size_t)nv * 3);
-    if (nrm) data->normals.assign(nrm, nrm + (size_t)nv * 3);
-    if (uv) data->texcoords.assign(uv, uv + (size_t)nv * 2);
-    data->indices.assign(idx, idx + (size_t)nf * 3);
-    for (size_t i = 0; i < (size_t)nv * 3; i += 3) data->aabb.Merge(util::Float3{ pos[i], pos[i + 1], pos[i + 2] });
+    if (borrow) {
+        data->pos = pos, data->nrm = nrm, data->uv = uv, data->idx = idx;
+    } else {
+        data->positions.assign(pos, pos + (size_t)nv * 3);
+        if (nrm) data->normals.assign(nrm, nrm + (size_t)nv * 3);
+        if (uv) data->texcoords.assign(uv, uv + (size_t)nv * 2);
+        data->indices.assign(idx, idx + (size_t)nf * 3);
+        data->pos = data->positions.data(), data->nrm = nrm ? data->normals.data() : nullptr;
+        data->uv = uv ? data->texcoords.data() : nullptr, data->idx = data->indices.data();
+    }
+    data->nv = nv, data->nf = nf;
+    data->aabb = BoundsOf(data->pos, nv);
     Shape *s = MakeMeshShape(key, EShapeType::_obj, *data);
     m_meshes[key] = std::move(data), m_mesh_shape[key] = s;
     return s;
+}
+void ShapeManager::DropMeshShape(std::string_view key_) noexcept {
+    const std::string key(key_);
+    auto it = m_mesh_shape.find(key);
+    if (it == m_mesh_shape.end()) return;
+    m_id_shapes.erase(it->second->id);
+    m_mesh_shape.erase(it);
+    m_meshes.erase(key);
 }
 Shape *ShapeManager::LoadSphere() noexcept {
     if (m_sphere) return m_sphere;

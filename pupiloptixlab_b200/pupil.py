@@ -58,6 +58,7 @@ def lib():
             "pupil_get_env_tables": [P(u32), P(u32), vp, vp, vp], "pupil_set_instance_transform": [u32, P(f32)],
             "pupil_remove_instance": [u32], "pupil_comm_unique_id": [vp], "pupil_set_shard": [C.c_int, C.c_int, vp, C.c_int, C.c_int],
             "pupil_synchronize": [], "pupil_set_shard_plan": [C.c_int],
+            "pupil_register_mesh_borrowed": [C.c_char_p, vp, vp, vp, vp, u32, u32], "pupil_unregister_mesh": [C.c_char_p],
             "pupil_checkpoint_save": [C.c_char_p], "pupil_checkpoint_load": [C.c_char_p],
         }
         for name, args in sigs.items():
@@ -95,10 +96,16 @@ def parse_scene_xml(path):
     check(lib().pupil_parse_scene_xml(str(path).encode()))
 
 
-def load_scene(desc: SceneDesc, host_only: bool = False):
-    """SceneDesc -> XML text (in memory) -> the host library's loader; triangle meshes go across as arrays."""
-    global _mesh_serial
-    names = {}
+_borrowed = {}  # key -> the arrays a borrowed registration points at (kept alive here), of the scene loaded last
+
+
+def load_scene(desc: SceneDesc, host_only: bool = False, borrow: bool = True):
+    """SceneDesc -> XML text (in memory) -> the host library's loader; triangle meshes go across as arrays.
+    borrow: the library points at the arrays instead of copying them (pupil_register_mesh_borrowed); this module keeps them
+    alive until the next scene is loaded.  Arrays that live in pinned memory (e.g. numpy views of pinned torch tensors) make
+    the upload a straight DMA."""
+    global _mesh_serial, _borrowed
+    names, keep = {}, {}
     for i, sh in enumerate(desc.shapes):
         if sh.type != "obj":
             continue
@@ -109,14 +116,22 @@ def load_scene(desc: SceneDesc, host_only: bool = False):
         I = np.ascontiguousarray(m["indices"], np.uint32).reshape(-1, 3)
         N = None if m.get("normals") is None else np.ascontiguousarray(m["normals"], np.float32)
         T = None if m.get("texcoords") is None else np.ascontiguousarray(m["texcoords"], np.float32)
-        check(lib().pupil_register_mesh(key.encode(), pb2._ptr(P), pb2._ptr(N), pb2._ptr(T), pb2._ptr(I), P.shape[0], I.shape[0]))
+        fn = lib().pupil_register_mesh_borrowed if borrow else lib().pupil_register_mesh
+        check(fn(key.encode(), pb2._ptr(P), pb2._ptr(N), pb2._ptr(T), pb2._ptr(I), P.shape[0], I.shape[0]))
         names[i] = key
+        if borrow:
+            keep[key] = (P, I, N, T)
     from . import scenes as _scenes
     for t in _scenes.images_of(desc):  # bitmap textures / env maps that carry their texels in memory
         img = np.ascontiguousarray(t.image, np.float32)
         check(lib().pupil_register_image(_scenes.image_name(t).encode(), pb2._ptr(img), img.shape[1], img.shape[0]))
     fn = lib().pupil_parse_scene_xml_string if host_only else lib().pupil_load_scene_xml_string
-    check(fn(to_xml_string(desc, names).encode(), None))
+    try:
+        check(fn(to_xml_string(desc, names).encode(), None))
+    finally:
+        for key in _borrowed:  # the previous scene's render objects are gone now (or the load failed and left no scene)
+            lib().pupil_unregister_mesh(key.encode())
+        _borrowed = keep
 
 
 IMAGE_FORMATS = dict(hdr=0, exr=1, pfm=2, png=3, png_aces=4)
