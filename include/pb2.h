@@ -117,7 +117,11 @@ typedef struct pb2_build_stats {
     uint64_t bvh_bytes;    /* nodes + primitive records */
     float build_ms;        /* device time, CUDA events around the whole build */
     float sah_cost;        /* SAH cost of the wide tree (node cost 1, primitive cost 1), root area normalised */
-    uint32_t max_depth;    /* depth of the wide tree */
+    uint32_t max_depth;    /* depth of the wide tree (two-level: top level + 1 + deepest bottom-level tree) */
+    uint32_t n_blas;       /* bottom-level trees (meshes reached through instance nodes); 0 = everything flattened to world space */
+    uint64_t n_instance_leaves; /* placements of those meshes in the top level */
+    float top_level_ms;    /* the top-level part of build_ms (all of it after pb2_scene_set_instance_transform) */
+    uint32_t pad0;
 } pb2_build_stats;
 
 typedef struct pb2_render_stats {
@@ -181,9 +185,16 @@ int pb2_scene_set_emitters(pb2_scene *scene, const pb2_emitter *areas, uint32_t 
 /* CameraHelper::GetCudaMemory (framework/world/camera.cpp:72-93): two row-major 4x4 */
 int pb2_scene_set_camera(pb2_scene *scene, const float sample_to_camera[16], const float camera_to_world[16]);
 
-/* replaces GAS::Create + IAS::Create (framework/world/gas_manager.cpp:69-245, ias_manager.cpp:29-114):
- * GPU build of one world-space compressed 8-wide BVH over every instance.  stats may be NULL. */
+/* replaces GAS::Create + IAS::Create / IAS::Update (framework/world/gas_manager.cpp:69-245, ias_manager.cpp:29-151): GPU build of
+ * the compressed 8-wide BVH.  Two levels, as in the reference: a mesh that is placed more than once (option instancing = 1, the
+ * default; 2 = every mesh of at least 64 triangles; 0 = none) gets ONE bottom-level tree in object space, shared by all its
+ * placements (GASManager::RefGAS, gas_manager.cpp:10); the top level holds an instance node per placement next to the
+ * world-space triangles of everything else and the analytic spheres.  After pb2_scene_set_instance_transform only the top
+ * level is rebuilt (stats->top_level_ms).  stats may be NULL. */
 int pb2_bvh_build(pb2_scene *scene, pb2_build_stats *stats);
+/* RenderObject::UpdateTransform -> IASManager::UpdateInstance (framework/world/render_object.cpp:72-80, ias_manager.cpp:116-151):
+ * new 3x4 object->world transform of one instance; the next pb2_bvh_build keeps every bottom-level tree */
+int pb2_scene_set_instance_transform(pb2_scene *scene, uint32_t instance_id, const float xform[12]);
 /* builder: 0 = LBVH over 63-bit Morton codes; 1 = binned-SAH sweep along the Morton order (16 equal-count bins per node, exact
  * sweep below 17 primitives; bvh_sah.cu — measured worse than LBVH: splits that do not fall on octree-cell boundaries of the
  * Z-curve produce overlapping boxes); 2 = SAH-driven bottom-up clustering (bvh_ploc.cu): mutual nearest neighbours by the
@@ -214,7 +225,7 @@ int pb2_render_stats_get(pb2_scene *scene, pb2_render_stats *stats); /* synchron
  * material type; default -1), refill_threshold (persistent traversal), shade_variant (4 | 6 | 7 | 8 resident CTAs per SM),
  * two_lanes (two batches in flight on two streams), coop_prims (warp-cooperative primitive tests: 1 on, 0 off, -1 = auto
  * by scene size), l2_persist_mb / l2_window_mb (persisting-L2 access-policy window over the top levels of the node array;
- * 0 = off, the default), ploc_radius (builder 2: neighbours searched on either side, 1..16, default 8).  Unknown names fail
+ * 0 = off, the default), ploc_radius (builder 2: neighbours searched on either side, 1..16, default 8), instancing (0 | 1 | 2, see pb2_bvh_build).  Unknown names fail
  * with PB2_ERR_ARG. */
 int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value);
 /* frame[i] = (sum[i].xyz / total_spp, 1) on the scene's stream: the last step of a sharded render whose sums were combined

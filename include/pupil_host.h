@@ -103,6 +103,9 @@ int pupil_get_emitters(pb2_emitter *areas, pb2_emitter *env, int32_t *has_env);
 /* World::GetSceneHandle(): the pb2 scene (BVH built, camera and emitters uploaded) for pb2_trace_* etc. */
 int pupil_scene_handle(pb2_scene **scene);
 int pupil_set_bvh_builder(int builder);
+/* World::SetInstancing: 0 flatten every shape, 1 bottom-level trees for shapes used by more than one render object (default), 2 for
+ * every mesh (transform edits then never rebuild more than the top level) */
+int pupil_set_instancing(int mode);
 int pupil_build_stats(pb2_build_stats *stats);
 int pupil_render_stats(pb2_render_stats *stats);
 /* camera edits through CameraHelper (framework/world/camera.cpp): mark the pass dirty like the GUI does */

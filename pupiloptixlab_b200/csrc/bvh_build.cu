@@ -51,9 +51,11 @@ __device__ __forceinline__ float half_area(float3 lo, float3 hi) {
 }
 
 // ---- stage 1 ---------------------------------------------------------------------------------------------
-// One thread per primitive.  inst_first[i] = index of the first primitive of instance i (n_inst+1 entries).
-__global__ void k_emit_prims(const DevInstance *__restrict__ inst, const uint32_t *__restrict__ inst_first, uint32_t n_inst, uint32_t n_prims,
-                             PrimRec *__restrict__ prims, float4 *__restrict__ box_lo, float4 *__restrict__ box_hi, int *__restrict__ scene_bounds) {
+// One thread per primitive.  inst_first[i] = index of the first primitive of the i-th LISTED instance (n_inst+1 entries);
+// inst_ids[i] = which instance of the scene that is (nullptr: the i-th).  A bottom-level build lists one instance with the
+// identity transform (object-space records), the top-level build lists the instances that are flattened into it.
+__global__ void k_emit_prims(const DevInstance *__restrict__ inst, const uint32_t *__restrict__ inst_first, const uint32_t *__restrict__ inst_ids, uint32_t n_inst,
+                             uint32_t n_prims, PrimRec *__restrict__ prims, float4 *__restrict__ box_lo, float4 *__restrict__ box_hi, int *__restrict__ scene_bounds) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     float3 lo = mk3(FLT_MAX), hi = mk3(-FLT_MAX);
     if (g < n_prims) {
@@ -63,8 +65,9 @@ __global__ void k_emit_prims(const DevInstance *__restrict__ inst, const uint32_
             if (inst_first[m] <= g) a = m;
             else b = m;
         }
-        const DevInstance &in = inst[a];
         const uint32_t prim = g - inst_first[a];
+        if (inst_ids) a = inst_ids[a];
+        const DevInstance &in = inst[a];
         PrimRec r;
         if (in.flags & PB2_IF_SPHERE) {
             // exact bounds of the affinely transformed unit sphere: centre +- row norms
@@ -119,6 +122,25 @@ __global__ void k_emit_prims(const DevInstance *__restrict__ inst, const uint32_
             }
         }
     }
+}
+
+// Instance leaves of a top-level build: one record per placement of a mesh that has its own bottom-level tree.
+//   record: v0.w = bits(root node of that tree in the scene's node array), e1.w = bits(instance id), e2.w = bits(2)
+// The collapse turns each of them into an instance node (traverse.cuh); the record itself is never intersected.
+__global__ void k_emit_instance_leaves(uint32_t n, uint32_t first, const float4 *__restrict__ lo, const float4 *__restrict__ hi, const uint32_t *__restrict__ root_node,
+                                       const uint32_t *__restrict__ inst_id, PrimRec *__restrict__ prims, float4 *__restrict__ box_lo, float4 *__restrict__ box_hi,
+                                       int *__restrict__ scene_bounds) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PrimRec r;
+    r.v0 = make_float4(0.f, 0.f, 0.f, __uint_as_float(root_node[i]));
+    r.e1 = make_float4(0.f, 0.f, 0.f, __uint_as_float(inst_id[i]));
+    r.e2 = make_float4(0.f, 0.f, 0.f, __uint_as_float(2u));
+    prims[first + i] = r;
+    const float4 l = lo[i], h = hi[i];
+    box_lo[first + i] = l, box_hi[first + i] = h;
+    atomicMin(&scene_bounds[0], float_to_ordered(l.x)), atomicMin(&scene_bounds[1], float_to_ordered(l.y)), atomicMin(&scene_bounds[2], float_to_ordered(l.z));
+    atomicMax(&scene_bounds[3], float_to_ordered(h.x)), atomicMax(&scene_bounds[4], float_to_ordered(h.y)), atomicMax(&scene_bounds[5], float_to_ordered(h.z));
 }
 
 // ---- stage 2 -------------------------------------------------------------------------------------------
@@ -191,8 +213,11 @@ __global__ void k_radix_tree(const uint64_t *__restrict__ keys, BinTree t) {
 }
 
 // ---- stage 4 ---------------------------------------------------------------------------------------------
+// weight_src != nullptr (top-level build with instance leaves): range.y becomes a WEIGHTED primitive count in which an instance
+// leaf counts kLeafMax + 1, so no subtree that holds one is ever folded into a leaf slot and the collapse reaches it on its own.
+__device__ __forceinline__ int leaf_weight(const PrimRec *prims, uint32_t p) { return __float_as_uint(prims[p].e2.w) == 2u ? kLeafMax + 1 : 1; }
 __global__ void k_refit(BinTree t, const uint32_t *__restrict__ sorted, const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi,
-                        int *__restrict__ arrive) {
+                        int *__restrict__ arrive, const PrimRec *__restrict__ weight_src) {
     const int n = t.n, j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     int node = t.parent[(n - 1) + j];
@@ -208,6 +233,11 @@ __global__ void k_refit(BinTree t, const uint32_t *__restrict__ sorted, const fl
         const float3 lo = fmin3(llo, rlo), hi = fmax3(lhi, rhi);
         t.lo[node] = make_float4(lo.x, lo.y, lo.z, 0.f);
         t.hi[node] = make_float4(hi.x, hi.y, hi.z, 0.f);
+        if (weight_src) {
+            const int wl = lc >= 0 ? __ldcg(&t.range[lc]).y : leaf_weight(weight_src, sorted[~lc]);
+            const int wr = rc >= 0 ? __ldcg(&t.range[rc]).y : leaf_weight(weight_src, sorted[~rc]);
+            t.range[node].y = wl + wr;
+        }
         __threadfence();
         node = t.parent[node];
     }
@@ -223,6 +253,7 @@ struct CollapseCtx {
     Bvh8Node *nodes;
     uint32_t *counters; // [0] nodes allocated, [1] prims allocated, [2] next-level queue size, [3] max depth
     float *sah;         // [0] accumulated SAH cost (un-normalised)
+    bool inst_leaves;   // top-level build: primitive records of kind 2 become instance nodes
 };
 struct Ref {
     float3 lo, hi;
@@ -239,7 +270,7 @@ __device__ __forceinline__ Ref load_ref(const CollapseCtx &c, int ref) {
     } else {
         const uint32_t p = c.sorted[~ref];
         r.lo = mk3(c.box_lo[p]), r.hi = mk3(c.box_hi[p]);
-        r.count = 1;
+        r.count = c.inst_leaves ? leaf_weight(c.prims_in, p) : 1;
     }
     return r;
 }
@@ -258,8 +289,10 @@ __device__ __forceinline__ int collect_leaves(const CollapseCtx &c, int ref, int
 __global__ void __launch_bounds__(256) k_scatter_prims(const PrimRec *__restrict__ prims_in, const uint32_t *__restrict__ sorted,
                                                         const uint32_t *__restrict__ dst_of_sorted, uint32_t n, PrimRec *__restrict__ prims_out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t d = dst_of_sorted[i];
+        if (d == 0xffffffffu) continue; // an instance leaf: it became a node, not a primitive
         const float4 *src = reinterpret_cast<const float4 *>(prims_in + sorted[i]);
-        float4 *dst = reinterpret_cast<float4 *>(prims_out + dst_of_sorted[i]);
+        float4 *dst = reinterpret_cast<float4 *>(prims_out + d);
         const float4 a = __ldg(src), b = __ldg(src + 1), cc = __ldg(src + 2);
         dst[0] = a, dst[1] = b, dst[2] = cc;
     }
@@ -277,7 +310,9 @@ __global__ void __launch_bounds__(128, PB2_COLLAPSE_MINB) k_collapse(CollapseCtx
     const Ref self = load_ref(c, (int)item.y);
     Ref ch[8];
     int n = 0;
-    if (self.ref >= 0 && self.count > 1) {
+    const bool is_instance = c.inst_leaves && self.ref < 0 && self.count > kLeafMax; // writes an instance node, has no children
+    if (is_instance) {
+    } else if (self.ref >= 0 && self.count > 1) {
         ch[n++] = load_ref(c, c.t.left[self.ref]);
         ch[n++] = load_ref(c, c.t.right[self.ref]);
         // expand the child with the largest surface area while slots remain; a child can be expanded
@@ -426,6 +461,13 @@ __global__ void __launch_bounds__(128, PB2_COLLAPSE_MINB) k_collapse(CollapseCtx
     node.n2 = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
     node.n3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
     node.n4 = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    if (is_instance) { // traverse.cuh: tag in the exponent / mask word, bottom-level root and instance id in n1
+        const PrimRec rec = c.prims_in[c.sorted[~self.ref]];
+        node.n0 = make_float4(0.f, 0.f, 0.f, __uint_as_float(0xffffffffu));
+        node.n1 = make_uint4(__float_as_uint(rec.v0.w), __float_as_uint(rec.e1.w), 0u, 0u);
+        node.n2 = node.n3 = node.n4 = make_uint4(0u, 0u, 0u, 0u);
+        sah_local = 0.f;
+    }
     c.nodes[item.x] = node;
     __syncwarp(warp_mask);
 #pragma unroll
@@ -445,6 +487,14 @@ bool sah_builder_available();
 void build_binary_sah(cudaStream_t st, uint32_t n, const float4 *box_lo, const float4 *box_hi, const uint32_t *sorted, int *left, int *right, int2 *range,
                       float4 *lo, float4 *hi);
 
+// a level's nodes, built with indices relative to the level, into their place in the scene's node array
+__global__ void __launch_bounds__(256) k_relocate_nodes(const Bvh8Node *__restrict__ src, uint32_t n, uint32_t node_offset, uint32_t prim_offset, Bvh8Node *__restrict__ dst) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        Bvh8Node nd = src[i];
+        if (__float_as_uint(nd.n0.w) != 0xffffffffu) nd.n1.x += node_offset, nd.n1.y += prim_offset; // instance nodes hold scene-wide indices already
+        dst[node_offset + i] = nd;
+    }
+}
 // largest vertex index of an index buffer (pb2_scene_add_mesh rejects meshes that point past their vertex arrays)
 __global__ void __launch_bounds__(256) k_max_index(const uint32_t *__restrict__ idx, uint64_t n, uint32_t *__restrict__ out) {
     uint32_t m = 0;
@@ -464,58 +514,26 @@ uint32_t max_index_dev(const uint32_t *idx, uint64_t n, cudaStream_t st) {
     return h;
 }
 
-void build_bvh(Scene &s) {
-    cudaStream_t st = s.stream;
-    s.upload_tables();
-    s.bvh_valid = false;
-    s.n_nodes = s.n_prims = 0;
-    s.build_stats = pb2_build_stats{};
+namespace {
+constexpr uint32_t kBlasMinTris = 64; // smaller shared meshes are flattened into the top level: an instance step costs more than their triangles
 
-    const uint32_t n_inst = (uint32_t)s.h_inst.size();
-    std::vector<uint32_t> first(n_inst + 1, 0);
-    uint64_t total = 0, n_sph = 0;
-    for (uint32_t i = 0; i < n_inst; ++i) {
-        first[i] = (uint32_t)total;
-        total += s.h_inst[i].n_tris;
-        if (s.h_inst[i].flags & PB2_IF_SPHERE) ++n_sph;
-    }
-    first[n_inst] = (uint32_t)total;
-    if (total >= 0x7fffffffull) throw std::runtime_error("pb2_bvh_build: more than 2^31-1 primitives");
-    const uint32_t n = (uint32_t)total;
-    s.build_stats.n_prims = n, s.build_stats.n_spheres = n_sph, s.build_stats.n_triangles = n - n_sph;
-    if (n == 0) {
-        s.bvh_valid = true;
-        return;
-    }
-    cudaEvent_t e0, e1;
-    PB2_CUDA(cudaEventCreate(&e0));
-    PB2_CUDA(cudaEventCreate(&e1));
-    PB2_CUDA(cudaEventRecord(e0, st));
+struct LevelOut {
+    DevBuf<Bvh8Node> nodes; // relative indices; relocated into the scene's array by the caller
+    uint32_t n_nodes = 0, n_prims_out = 0, depth = 0;
+    float sah = 0.f, lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+};
 
-    DevBuf<uint32_t> d_first(n_inst + 1);
-    d_first.upload(first.data(), n_inst + 1, st);
-    DevBuf<PrimRec> prims_in(n);
-    DevBuf<float4> box_lo(n), box_hi(n);
-    DevBuf<int> bounds(6);
-    {
-        int init[6];
-        float mx = FLT_MAX, mn = -FLT_MAX;
-        int imx, imn;
-        memcpy(&imx, &mx, 4), memcpy(&imn, &mn, 4);
-        imn = imn ^ 0x7fffffff; // ordered encoding of -FLT_MAX
-        for (int k = 0; k < 3; ++k) init[k] = imx, init[3 + k] = imn;
-        PB2_CUDA(cudaMemcpyAsync(bounds.ptr, init, sizeof init, cudaMemcpyHostToDevice, st));
-    }
-    k_emit_prims<<<div_up(n, 256), 256, 0, st>>>(s.d_inst.ptr, d_first.ptr, n_inst, n, prims_in.ptr, box_lo.ptr, box_hi.ptr, bounds.ptr);
-    PB2_LAUNCH_CHECK();
-
+// Stages 2-5 over n emitted records (prims_in, box_lo / box_hi, bounds): Morton sort, binary tree, collapse, scatter of the
+// records into prims_out (their final place).  inst_leaves: records of kind 2 become instance nodes (top level of a two-level scene).
+void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, DevBuf<PrimRec> &prims_in, DevBuf<float4> &box_lo, DevBuf<float4> &box_hi,
+                 DevBuf<int> &bounds, PrimRec *prims_out, LevelOut &out) {
+    const bool inst_leaves = n_inst_leaves > 0;
     DevBuf<uint32_t> sorted(n);
     DevBuf<int> left(n), right(n), parent(2 * (size_t)n);
     DevBuf<int2> range(n);
     DevBuf<float4> nlo(n), nhi(n);
     BinTree t{ left.ptr, right.ptr, parent.ptr, range.ptr, nlo.ptr, nhi.ptr, n };
     int root_ref = 0; // binary node the collapse starts from (node 0 for the top-down builders)
-
     {
         DevBuf<uint64_t> keys(n), keys_sorted(n);
         DevBuf<uint32_t> vals(n);
@@ -525,10 +543,11 @@ void build_bvh(Scene &s) {
         PB2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.ptr, keys_sorted.ptr, vals.ptr, sorted.ptr, (int)n, 0, 63, st));
         DevBuf<uint8_t> tmp(tmp_bytes);
         PB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys.ptr, keys_sorted.ptr, vals.ptr, sorted.ptr, (int)n, 0, 63, st));
-        if (n > 1 && s.builder == 2) {
+        // a top level with instance leaves needs the weighted counts of k_refit: it always takes the LBVH path (it is small)
+        if (n > 1 && s.builder == 2 && !inst_leaves) {
             // bottom-up clustering by the surface area of the union (bvh_ploc.cu); node boxes come out of the merges
             root_ref = build_binary_ploc(st, n, box_lo.ptr, box_hi.ptr, sorted.ptr, left.ptr, right.ptr, range.ptr, nlo.ptr, nhi.ptr, s.ploc_radius, nullptr);
-        } else if (n > 1 && s.builder == 1 && sah_builder_available()) {
+        } else if (n > 1 && s.builder == 1 && !inst_leaves && sah_builder_available()) {
             // binned SAH over the Morton-ordered sequence (bvh_sah.cu); node boxes come out of the sweep
             build_binary_sah(st, n, box_lo.ptr, box_hi.ptr, sorted.ptr, left.ptr, right.ptr, range.ptr, nlo.ptr, nhi.ptr);
         } else if (n > 1) {
@@ -536,15 +555,13 @@ void build_bvh(Scene &s) {
             PB2_LAUNCH_CHECK();
             DevBuf<int> arrive(n);
             arrive.zero(st);
-            k_refit<<<div_up(n, 256), 256, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr);
+            k_refit<<<div_up(n, 256), 256, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr, inst_leaves ? prims_in.ptr : nullptr);
             PB2_LAUNCH_CHECK();
         }
         PB2_CUDA(cudaStreamSynchronize(st)); // tmp / arrive / keys go out of scope
     }
-
     // ---- collapse ----
-    DevBuf<Bvh8Node> nodes(n); // upper bound: one wide node per binary internal node (+ root)
-    s.d_prims.alloc(n);
+    out.nodes.alloc((size_t)n + n_inst_leaves + 1); // upper bound: one wide node per binary internal node (+ root) + one instance node per instance leaf
     DevBuf<uint32_t> counters(4);
     DevBuf<float> sah(1);
     sah.zero(st);
@@ -554,10 +571,11 @@ void build_bvh(Scene &s) {
     uint4 root = make_uint4(0u, n > 1 ? (uint32_t)root_ref : (uint32_t)~0, 0u, 0u); // n == 1: leaf ref ~0
     PB2_CUDA(cudaMemcpyAsync(qa.ptr, &root, sizeof root, cudaMemcpyHostToDevice, st));
     DevBuf<uint32_t> dst_of_sorted(n);
-    CollapseCtx cc{ t, sorted.ptr, box_lo.ptr, box_hi.ptr, prims_in.ptr, dst_of_sorted.ptr, nodes.ptr, counters.ptr, sah.ptr };
+    PB2_CUDA(cudaMemsetAsync(dst_of_sorted.ptr, 0xff, (size_t)n * sizeof(uint32_t), st)); // records that get no leaf slot (instance leaves) stay ~0
+    CollapseCtx cc{ t, sorted.ptr, box_lo.ptr, box_hi.ptr, prims_in.ptr, dst_of_sorted.ptr, out.nodes.ptr, counters.ptr, sah.ptr, inst_leaves };
     uint32_t n_in = 1;
     uint4 *q_in = qa.ptr, *q_out = qb.ptr;
-    uint32_t host_counters[4];
+    uint32_t host_counters[4] = { 0, 0, 0, 0 };
     while (n_in) {
         k_collapse<<<div_up(n_in, 128), 128, 0, st>>>(cc, q_in, n_in, q_out);
         PB2_LAUNCH_CHECK();
@@ -567,38 +585,243 @@ void build_bvh(Scene &s) {
         PB2_CUDA(cudaMemsetAsync(counters.ptr + 2, 0, sizeof(uint32_t), st));
         std::swap(q_in, q_out);
     }
-    s.n_nodes = host_counters[0], s.n_prims = host_counters[1];
-    if (s.n_prims != n) throw std::runtime_error("pb2_bvh_build: collapse lost primitives");
-    {
+    out.n_nodes = host_counters[0], out.n_prims_out = host_counters[1], out.depth = host_counters[3];
+    if (out.n_prims_out != n - n_inst_leaves) throw std::runtime_error("pb2_bvh_build: collapse lost primitives");
+    if (out.n_prims_out) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        k_scatter_prims<<<(unsigned)std::min<uint64_t>(div_up(n, 256), (uint64_t)sms * 8), 256, 0, st>>>(prims_in.ptr, sorted.ptr, dst_of_sorted.ptr, n, s.d_prims.ptr);
+        k_scatter_prims<<<(unsigned)std::min<uint64_t>(div_up(n, 256), (uint64_t)sms * 8), 256, 0, st>>>(prims_in.ptr, sorted.ptr, dst_of_sorted.ptr, n, prims_out);
         PB2_LAUNCH_CHECK();
     }
-    // shrink the node array to its final size
-    s.d_nodes.alloc(s.n_nodes);
-    PB2_CUDA(cudaMemcpyAsync(s.d_nodes.ptr, nodes.ptr, s.n_nodes * sizeof(Bvh8Node), cudaMemcpyDeviceToDevice, st));
-    float sah_host = 0.f, root_area = 1.f;
+    float sah_host = 0.f;
     int hb[6];
     PB2_CUDA(cudaMemcpyAsync(&sah_host, sah.ptr, sizeof(float), cudaMemcpyDeviceToHost, st));
     PB2_CUDA(cudaMemcpyAsync(hb, bounds.ptr, sizeof hb, cudaMemcpyDeviceToHost, st));
+    PB2_CUDA(cudaStreamSynchronize(st));
+    for (int k = 0; k < 3; ++k) out.lo[k] = ordered_to_float(hb[k]), out.hi[k] = ordered_to_float(hb[3 + k]);
+    const float d[3] = { out.hi[0] - out.lo[0], out.hi[1] - out.lo[1], out.hi[2] - out.lo[2] };
+    const float root_area = d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
+    out.sah = root_area > 0.f ? sah_host / root_area : 0.f;
+}
+
+void init_bounds(DevBuf<int> &bounds, cudaStream_t st) {
+    int init[6];
+    float mx = FLT_MAX, mn = -FLT_MAX;
+    int imx, imn;
+    memcpy(&imx, &mx, 4), memcpy(&imn, &mn, 4);
+    imn = imn ^ 0x7fffffff; // ordered encoding of -FLT_MAX
+    for (int k = 0; k < 3; ++k) init[k] = imx, init[3 + k] = imn;
+    PB2_CUDA(cudaMemcpyAsync(bounds.ptr, init, sizeof init, cudaMemcpyHostToDevice, st));
+    PB2_CUDA(cudaStreamSynchronize(st)); // `init` is a stack array
+}
+}// namespace
+
+// Which meshes get a bottom-level tree of their own (Scene::instancing): 1 (default) = meshes placed more than once, as the
+// reference shares one GAS between the instances of a shape (gas_manager.cpp:10 RefGAS); 2 = every mesh, so that a transform
+// edit never rebuilds more than the top level (ias_manager.cpp:116-151 IAS::Update); 0 = none, everything flattened to world space.
+static bool wants_blas(const Scene &s, const Mesh &m, uint32_t uses) {
+    if (s.instancing == 0 || m.n_tris < kBlasMinTris) return false;
+    return s.instancing >= 2 ? uses >= 1 : uses >= 2;
+}
+
+void build_bvh(Scene &s) {
+    cudaStream_t st = s.stream;
+    s.upload_tables();
+    s.bvh_valid = false;
+    const uint32_t n_inst = (uint32_t)s.h_inst.size();
+    cudaEvent_t e0, e1;
+    PB2_CUDA(cudaEventCreate(&e0));
+    PB2_CUDA(cudaEventCreate(&e1));
+    PB2_CUDA(cudaEventRecord(e0, st));
+
+    // ---- which mesh of which instance ----
+    const std::vector<int> &mesh_of_inst = s.h_inst_mesh; // -1: analytic sphere
+    std::vector<uint32_t> uses(s.meshes.size(), 0);
+    for (uint32_t i = 0; i < n_inst; ++i)
+        if (mesh_of_inst[i] >= 0) ++uses[mesh_of_inst[i]];
+    // a finished top-level-only update keeps the bottom-level trees; anything else starts over
+    const bool tlas_only = s.blas_valid && s.n_blas > 0;
+    if (!tlas_only) {
+        for (auto &m : s.meshes) m->blas = Blas{};
+        s.n_blas = 0;
+    }
+    pb2_build_stats stats{};
+    std::vector<std::unique_ptr<LevelOut>> levels; // bottom-level trees built in this call, in mesh order
+    std::vector<size_t> level_mesh;
+    uint64_t blas_prims = 0, blas_nodes_cap = 0;
+    if (!tlas_only) {
+        for (size_t m = 0; m < s.meshes.size(); ++m)
+            if (wants_blas(s, *s.meshes[m], uses[m])) blas_prims += s.meshes[m]->n_tris;
+    } else {
+        for (auto &m : s.meshes)
+            if (m->blas.valid) blas_prims += m->blas.n_prims;
+    }
+    // ---- top-level census ----
+    std::vector<uint32_t> flat_ids, first;
+    std::vector<uint32_t> leaf_inst;
+    uint64_t n_flat = 0, n_sph = 0;
+    for (uint32_t i = 0; i < n_inst; ++i) {
+        const int m = mesh_of_inst[i];
+        const bool blas = m >= 0 && (tlas_only ? s.meshes[m]->blas.valid : wants_blas(s, *s.meshes[m], uses[m]));
+        if (blas) {
+            leaf_inst.push_back(i);
+            continue;
+        }
+        flat_ids.push_back(i), first.push_back((uint32_t)n_flat);
+        n_flat += s.h_inst[i].n_tris;
+        if (s.h_inst[i].flags & PB2_IF_SPHERE) ++n_sph;
+    }
+    first.push_back((uint32_t)n_flat);
+    const uint64_t n_top = n_flat + leaf_inst.size();
+    if (blas_prims + n_top >= 0x7fffffffull) throw std::runtime_error("pb2_bvh_build: more than 2^31-1 primitives");
+    stats.n_spheres = n_sph;
+    if (n_top == 0) {
+        s.n_nodes = s.n_prims = 0, s.root = 0, s.n_blas = 0, s.blas_valid = false;
+        s.d_nodes.release(), s.d_prims.release();
+        s.build_stats = stats;
+        s.bvh_valid = true;
+        cudaEventDestroy(e0), cudaEventDestroy(e1);
+        return;
+    }
+    // ---- primitive array: [bottom-level records, object space][top-level records, world space] ----
+    const uint32_t top_prim_offset = (uint32_t)blas_prims;
+    if (!tlas_only || s.d_prims.n < blas_prims + n_flat) {
+        if (tlas_only) throw std::runtime_error("pb2_bvh_build: top-level update with a changed primitive count (rebuild the scene)");
+        s.d_prims.alloc(blas_prims + n_flat);
+    }
+    // ---- bottom-level trees ----
+    uint32_t max_blas_depth = 0;
+    if (!tlas_only) {
+        uint32_t prim_cursor = 0;
+        for (size_t m = 0; m < s.meshes.size(); ++m) {
+            Mesh &mesh = *s.meshes[m];
+            if (!wants_blas(s, mesh, uses[m])) continue;
+            const uint32_t n = mesh.n_tris;
+            DevInstance ident{};
+            ident.xf[0] = ident.inv[0] = make_float4(1, 0, 0, 0), ident.xf[1] = ident.inv[1] = make_float4(0, 1, 0, 0), ident.xf[2] = ident.inv[2] = make_float4(0, 0, 1, 0);
+            ident.pos = mesh.pos.ptr, ident.nrm = mesh.nrm.ptr, ident.uv = mesh.uv.ptr, ident.idx = mesh.idx.ptr, ident.n_tris = n, ident.emitter_offset = -1;
+            DevBuf<DevInstance> d_ident(1);
+            d_ident.upload(&ident, 1, st);
+            const uint32_t firsts[2] = { 0u, n };
+            DevBuf<uint32_t> d_first(2);
+            d_first.upload(firsts, 2, st);
+            PB2_CUDA(cudaStreamSynchronize(st));
+            DevBuf<PrimRec> prims_in(n);
+            DevBuf<float4> box_lo(n), box_hi(n);
+            DevBuf<int> bounds(6);
+            init_bounds(bounds, st);
+            k_emit_prims<<<div_up(n, 256), 256, 0, st>>>(d_ident.ptr, d_first.ptr, nullptr, 1u, n, prims_in.ptr, box_lo.ptr, box_hi.ptr, bounds.ptr);
+            PB2_LAUNCH_CHECK();
+            auto lv = std::make_unique<LevelOut>();
+            build_level(s, st, n, 0, prims_in, box_lo, box_hi, bounds, s.d_prims.ptr + prim_cursor, *lv);
+            mesh.blas.valid = true, mesh.blas.prim_offset = prim_cursor, mesh.blas.n_prims = n, mesh.blas.n_nodes = lv->n_nodes, mesh.blas.depth = lv->depth;
+            for (int k = 0; k < 3; ++k) mesh.blas.lo[k] = lv->lo[k], mesh.blas.hi[k] = lv->hi[k];
+            prim_cursor += n;
+            blas_nodes_cap += lv->n_nodes;
+            levels.push_back(std::move(lv)), level_mesh.push_back(m);
+            ++s.n_blas;
+        }
+        uint32_t node_cursor = 0;
+        for (size_t k = 0; k < levels.size(); ++k) {
+            s.meshes[level_mesh[k]]->blas.node_offset = node_cursor;
+            node_cursor += levels[k]->n_nodes;
+        }
+        s.top_node_offset = node_cursor;
+    }
+    for (auto &m : s.meshes)
+        if (m->blas.valid) max_blas_depth = std::max(max_blas_depth, m->blas.depth), stats.n_nodes += m->blas.n_nodes, stats.n_triangles += m->blas.n_prims;
+
+    // ---- top level ----
+    cudaEvent_t t0;
+    PB2_CUDA(cudaEventCreate(&t0));
+    PB2_CUDA(cudaEventRecord(t0, st));
+    const uint32_t n = (uint32_t)n_top, n_leaves = (uint32_t)leaf_inst.size();
+    DevBuf<PrimRec> prims_in(n);
+    DevBuf<float4> box_lo(n), box_hi(n);
+    DevBuf<int> bounds(6);
+    init_bounds(bounds, st);
+    if (n_flat) {
+        DevBuf<uint32_t> d_first(first.size()), d_ids(flat_ids.size());
+        d_first.upload(first.data(), first.size(), st);
+        d_ids.upload(flat_ids.data(), flat_ids.size(), st);
+        k_emit_prims<<<div_up(n_flat, 256), 256, 0, st>>>(s.d_inst.ptr, d_first.ptr, d_ids.ptr, (uint32_t)flat_ids.size(), (uint32_t)n_flat, prims_in.ptr, box_lo.ptr,
+                                                          box_hi.ptr, bounds.ptr);
+        PB2_LAUNCH_CHECK();
+        PB2_CUDA(cudaStreamSynchronize(st));
+    }
+    if (n_leaves) { // world-space box of every placement: the eight corners of the bottom-level root box through the instance transform
+        std::vector<float4> lo(n_leaves), hi(n_leaves);
+        std::vector<uint32_t> roots(n_leaves);
+        for (uint32_t k = 0; k < n_leaves; ++k) {
+            const DevInstance &in = s.h_inst[leaf_inst[k]];
+            const Blas &b = s.meshes[mesh_of_inst[leaf_inst[k]]]->blas;
+            float l[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, h[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+            for (int c = 0; c < 8; ++c) {
+                const float p[3] = { c & 1 ? b.hi[0] : b.lo[0], c & 2 ? b.hi[1] : b.lo[1], c & 4 ? b.hi[2] : b.lo[2] };
+                for (int r = 0; r < 3; ++r) {
+                    const float4 row = in.xf[r];
+                    const float v = row.x * p[0] + row.y * p[1] + row.z * p[2] + row.w;
+                    l[r] = std::min(l[r], v), h[r] = std::max(h[r], v);
+                }
+            }
+            // the traversal transforms the RAY, in fp32: pad the box by a few ulps of its largest coordinate
+            float pad = 0.f;
+            for (int r = 0; r < 3; ++r) pad = std::max(pad, std::max(std::fabs(l[r]), std::fabs(h[r])));
+            pad *= 4e-7f;
+            lo[k] = make_float4(l[0] - pad, l[1] - pad, l[2] - pad, 0.f), hi[k] = make_float4(h[0] + pad, h[1] + pad, h[2] + pad, 0.f);
+            roots[k] = b.node_offset;
+        }
+        DevBuf<float4> d_lo(n_leaves), d_hi(n_leaves);
+        DevBuf<uint32_t> d_roots(n_leaves), d_ids(n_leaves);
+        d_lo.upload(lo.data(), n_leaves, st), d_hi.upload(hi.data(), n_leaves, st);
+        d_roots.upload(roots.data(), n_leaves, st), d_ids.upload(leaf_inst.data(), n_leaves, st);
+        k_emit_instance_leaves<<<div_up(n_leaves, 256), 256, 0, st>>>(n_leaves, (uint32_t)n_flat, d_lo.ptr, d_hi.ptr, d_roots.ptr, d_ids.ptr, prims_in.ptr, box_lo.ptr,
+                                                                      box_hi.ptr, bounds.ptr);
+        PB2_LAUNCH_CHECK();
+        PB2_CUDA(cudaStreamSynchronize(st));
+    }
+    LevelOut top;
+    build_level(s, st, n, n_leaves, prims_in, box_lo, box_hi, bounds, s.d_prims.ptr + top_prim_offset, top);
+    if (!tlas_only) {
+        // node array: [bottom-level trees][top level + room to grow: a top-level update after transform edits may need a few more
+        // wide nodes than this build did]
+        const uint64_t top_cap = std::min<uint64_t>(n_top + n_leaves + 1, (uint64_t)top.n_nodes + top.n_nodes / 2 + 64);
+        s.d_nodes.alloc((uint64_t)s.top_node_offset + top_cap);
+        for (size_t k = 0; k < levels.size(); ++k) {
+            const Blas &b = s.meshes[level_mesh[k]]->blas;
+            k_relocate_nodes<<<div_up(levels[k]->n_nodes, 256), 256, 0, st>>>(levels[k]->nodes.ptr, levels[k]->n_nodes, b.node_offset, b.prim_offset, s.d_nodes.ptr);
+            PB2_LAUNCH_CHECK();
+        }
+        s.blas_valid = s.n_blas > 0;
+    } else if ((uint64_t)s.top_node_offset + top.n_nodes > s.d_nodes.n) { // the update outgrew its room: build everything again
+        cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(t0);
+        s.blas_valid = false;
+        build_bvh(s);
+        return;
+    }
+    k_relocate_nodes<<<div_up(top.n_nodes, 256), 256, 0, st>>>(top.nodes.ptr, top.n_nodes, s.top_node_offset, top_prim_offset, s.d_nodes.ptr);
+    PB2_LAUNCH_CHECK();
     PB2_CUDA(cudaEventRecord(e1, st));
     PB2_CUDA(cudaStreamSynchronize(st));
-    {
-        float d[3];
-        for (int k = 0; k < 3; ++k) d[k] = ordered_to_float(hb[3 + k]) - ordered_to_float(hb[k]);
-        root_area = d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
-    }
-    float ms = 0.f;
+    float ms = 0.f, top_ms = 0.f;
     PB2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0), cudaEventDestroy(e1);
-    s.build_stats.n_nodes = s.n_nodes;
-    s.build_stats.bvh_bytes = (uint64_t)s.n_nodes * sizeof(Bvh8Node) + (uint64_t)s.n_prims * sizeof(PrimRec);
-    s.build_stats.build_ms = ms;
-    s.build_stats.sah_cost = root_area > 0.f ? sah_host / root_area : 0.f;
-    s.build_stats.max_depth = host_counters[3];
-    if (host_counters[3] > PB2_STACK_SIZE - 2) throw std::runtime_error("pb2_bvh_build: wide tree deeper than the traversal stack (" + std::to_string(host_counters[3]) + " levels)");
+    PB2_CUDA(cudaEventElapsedTime(&top_ms, t0, e1));
+    cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(t0);
+
+    s.root = s.top_node_offset;
+    s.n_nodes = s.top_node_offset + top.n_nodes;
+    s.n_prims = top_prim_offset + top.n_prims_out;
+    stats.n_triangles += n_flat - n_sph;
+    stats.n_prims = stats.n_triangles + n_sph;
+    stats.n_nodes += top.n_nodes;
+    stats.bvh_bytes = (uint64_t)s.n_nodes * sizeof(Bvh8Node) + (uint64_t)s.n_prims * sizeof(PrimRec);
+    stats.build_ms = ms;
+    stats.sah_cost = top.sah;
+    stats.max_depth = top.depth + (s.n_blas ? 1 + max_blas_depth : 0);
+    stats.n_blas = s.n_blas, stats.n_instance_leaves = n_leaves, stats.top_level_ms = top_ms;
+    s.build_stats = stats;
+    if (stats.max_depth > PB2_STACK_SIZE - 2) throw std::runtime_error("pb2_bvh_build: tree deeper than the traversal stack (" + std::to_string(stats.max_depth) + " levels)");
     s.bvh_valid = true;
     if (s.l2_persist_mb > 0) s.l2_dirty = true; // the node array moved
 }

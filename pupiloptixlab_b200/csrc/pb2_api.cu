@@ -145,7 +145,7 @@ SceneView Scene::view() const {
     SceneView v{};
     v.nodes = d_nodes.ptr, v.prims = d_prims.ptr, v.instances = d_inst.ptr, v.materials = d_mat.ptr;
     v.areas = d_areas.ptr, v.env = has_env ? d_env.ptr : nullptr, v.area_cdf = d_area_cdf.ptr;
-    v.n_areas = (uint32_t)h_areas.size(), v.n_nodes = n_nodes, v.n_prims = n_prims;
+    v.n_areas = (uint32_t)h_areas.size(), v.n_nodes = n_nodes, v.n_prims = n_prims, v.root = root;
     return v;
 }
 }// namespace pb2
@@ -395,8 +395,8 @@ int pb2_scene_clear(pb2_scene *scene) {
     PB2_TRY
     Scene &s = *S(scene);
     PB2_CUDA(cudaStreamSynchronize(s.stream));
-    s.meshes.clear(), s.h_inst.clear(), s.h_mat.clear(), s.h_areas.clear();
-    s.has_env = false, s.tables_dirty = true, s.bvh_valid = false, s.n_nodes = s.n_prims = 0;
+    s.meshes.clear(), s.h_inst.clear(), s.h_inst_mesh.clear(), s.h_mat.clear(), s.h_areas.clear();
+    s.has_env = false, s.tables_dirty = true, s.bvh_valid = false, s.blas_valid = false, s.n_blas = 0, s.root = 0, s.n_nodes = s.n_prims = 0;
     s.d_nodes.release(), s.d_prims.release();
     return PB2_OK;
     PB2_CATCH
@@ -426,6 +426,7 @@ int pb2_scene_add_mesh(pb2_scene *scene, const float *pos, const float *nrm, con
     if (max_idx >= n_vertices) return fail(PB2_ERR_ARG, "pb2_scene_add_mesh: vertex index " + std::to_string(max_idx) + " >= n_vertices " + std::to_string(n_vertices));
     if (mesh_id) *mesh_id = (uint32_t)s.meshes.size();
     s.meshes.push_back(std::move(m));
+    s.blas_valid = false;
     return PB2_OK;
     PB2_CATCH
 }
@@ -460,8 +461,25 @@ int pb2_scene_add_instance(pb2_scene *scene, uint32_t mesh_id, const float xform
     in.emitter_offset = emitter_index_offset;
     if (instance_id) *instance_id = (uint32_t)s.h_inst.size();
     s.h_inst.push_back(in);
+    s.h_inst_mesh.push_back(mesh_id == PB2_MESH_SPHERE ? -1 : (int)mesh_id);
     s.h_mat.push_back(to_dev(mat));
-    s.tables_dirty = true, s.bvh_valid = false;
+    s.tables_dirty = true, s.bvh_valid = false, s.blas_valid = false; // how often a mesh is placed decides whether it gets a tree of its own
+    return PB2_OK;
+    PB2_CATCH
+}
+int pb2_scene_set_instance_transform(pb2_scene *scene, uint32_t instance_id, const float xform[12]) {
+    PB2_TRY
+    if (!scene || !xform) return fail(PB2_ERR_ARG, "pb2_scene_set_instance_transform: null");
+    Scene &s = *S(scene);
+    if (instance_id >= s.h_inst.size()) return fail(PB2_ERR_ARG, "pb2_scene_set_instance_transform: no such instance");
+    float inv[12];
+    if (!invert_affine(xform, inv)) return fail(PB2_ERR_ARG, "pb2_scene_set_instance_transform: singular transform");
+    DevInstance &in = s.h_inst[instance_id];
+    for (int r = 0; r < 3; ++r) {
+        in.xf[r] = make_float4(xform[r * 4], xform[r * 4 + 1], xform[r * 4 + 2], xform[r * 4 + 3]);
+        in.inv[r] = make_float4(inv[r * 4], inv[r * 4 + 1], inv[r * 4 + 2], inv[r * 4 + 3]);
+    }
+    s.tables_dirty = true, s.bvh_valid = false; // blas_valid stays: pb2_bvh_build rebuilds the top level only
     return PB2_OK;
     PB2_CATCH
 }
@@ -597,6 +615,7 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     else if (n == "two_lanes") s.two_lanes = value != 0;
     else if (n == "coop_prims") s.coop_prims = (int)std::min<int64_t>(1, std::max<int64_t>(-1, value));
     else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);
+    else if (n == "instancing") s.instancing = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)), s.bvh_valid = false, s.blas_valid = false;
     else if (n == "ploc_radius") s.ploc_radius = (int)std::min<int64_t>(16, std::max<int64_t>(1, value)), s.bvh_valid = false;
     else if (n == "l2_persist_mb") s.l2_persist_mb = (int)std::min<int64_t>(1024, std::max<int64_t>(0, value)), s.l2_dirty = true;
     else if (n == "l2_window_mb") s.l2_window_mb = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value)), s.l2_dirty = true;

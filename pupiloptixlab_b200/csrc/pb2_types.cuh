@@ -86,5 +86,6 @@ struct SceneView {
     uint32_t n_areas;
     uint32_t n_nodes;
     uint32_t n_prims;
+    uint32_t root; // node the traversal starts at: the top-level tree's root (it sits behind the bottom-level trees in `nodes`)
 };
 }// namespace pb2

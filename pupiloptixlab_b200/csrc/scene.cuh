@@ -8,10 +8,18 @@
 
 namespace pb2 {
 
+// bottom-level tree of a mesh that is placed through instance nodes (bvh_build.cu): object-space records and nodes inside the
+// scene's arrays — GAS of the reference (framework/world/gas_manager.cpp)
+struct Blas {
+    bool valid = false;
+    uint32_t node_offset = 0, n_nodes = 0, prim_offset = 0, n_prims = 0, depth = 0;
+    float lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 }; // object-space bounds of the root
+};
 struct Mesh {
     DevBuf<float> pos, nrm, uv;
     DevBuf<uint32_t> idx;
     uint32_t n_verts = 0, n_tris = 0;
+    Blas blas;
 };
 
 struct Wavefront; // wavefront.cu
@@ -20,6 +28,7 @@ struct Scene {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::vector<std::unique_ptr<Mesh>> meshes;
     std::vector<DevInstance> h_inst;
+    std::vector<int> h_inst_mesh; // mesh id of every instance (-1: analytic sphere)
     std::vector<DevMaterial> h_mat;
     std::vector<DevEmitter> h_areas;
     bool has_env = false;
@@ -37,6 +46,11 @@ struct Scene {
     DevBuf<uint32_t> trace_work; // work counter of the persistent trace kernels
     uint32_t n_nodes = 0, n_prims = 0;
     bool bvh_valid = false;
+    // two-level structure (bvh_build.cu): meshes with a bottom-level tree are reached through instance nodes of the top level
+    int instancing = 1;          // 0 flatten everything, 1 bottom-level trees for meshes placed more than once, 2 for every mesh
+    uint32_t n_blas = 0;         // bottom-level trees in the node array
+    uint32_t top_node_offset = 0, root = 0; // the top level sits behind them; traversal starts at `root`
+    bool blas_valid = false;     // the bottom-level trees match the meshes and instances: only the top level needs rebuilding
     int builder = 0; // 0 LBVH, 1 binned SAH sweep along the Morton order, 2 SAH-driven bottom-up clustering (bvh_ploc.cu)
     int ploc_radius = 8; // neighbours searched on either side along the Morton curve (builder 2)
     pb2_build_stats build_stats{};

@@ -17,7 +17,7 @@ struct ClosestIO {
         o = mk3(ro), d = mk3(rd), tmin = ro.w, tmax = rd.w;
         return i;
     }
-    PB2_D void commit(bool valid, uint32_t i, const RayHit &h, bool hit) const {
+    PB2_D void commit(bool valid, uint32_t i, const RayHit &h, bool hit, uint32_t inst_of_hit) const {
         if (!valid) return;
         int32_t inst = -1;
         uint32_t prim = 0xffffffffu;
@@ -25,7 +25,7 @@ struct ClosestIO {
         if (hit) {
             const float4 *rec = reinterpret_cast<const float4 *>(prims + h.prim_slot);
             prim = __float_as_uint(__ldg(rec).w);
-            inst = (int32_t)__float_as_uint(__ldg(rec + 1).w);
+            inst = inst_of_hit != 0xffffffffu ? (int32_t)inst_of_hit : (int32_t)__float_as_uint(__ldg(rec + 1).w);
             t = h.t;
         }
         hit_tuvp[i] = make_float4(t, h.u, h.v, __uint_as_float(prim));
@@ -42,24 +42,24 @@ struct AnyIO {
         o = mk3(ro), d = mk3(rd), tmin = ro.w, tmax = rd.w;
         return i;
     }
-    PB2_D void commit(bool valid, uint32_t i, const RayHit &, bool hit) const {
+    PB2_D void commit(bool valid, uint32_t i, const RayHit &, bool hit, uint32_t) const {
         if (valid) occluded[i] = hit ? 1u : 0u;
     }
 };
 
-template<bool COUNT, bool COOP, bool TRIS = false>
+template<bool COUNT, bool COOP, bool TRIS = false, bool INST = false>
 __global__ void __launch_bounds__(128, PB2_TRACE_MINB(COOP)) k_trace_closest(SceneView sv, ClosestIO io, uint32_t *__restrict__ work, unsigned long long *__restrict__ counters, int thr) {
     TraceCounters ctr{ 0, 0 };
-    trace_persistent<false, COUNT, COOP, TRIS>(sv, io, work, &ctr, thr);
+    trace_persistent<false, COUNT, COOP, TRIS, INST>(sv, io, work, &ctr, thr);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)ctr.nodes);
         atomicAdd(&counters[1], (unsigned long long)ctr.prims);
     }
 }
-template<bool COUNT, bool COOP, bool TRIS = false>
+template<bool COUNT, bool COOP, bool TRIS = false, bool INST = false>
 __global__ void __launch_bounds__(128, PB2_TRACE_MINB(COOP)) k_trace_any(SceneView sv, AnyIO io, uint32_t *__restrict__ work, unsigned long long *__restrict__ counters, int thr) {
     TraceCounters ctr{ 0, 0 };
-    trace_persistent<true, COUNT, COOP, TRIS>(sv, io, work, &ctr, thr);
+    trace_persistent<true, COUNT, COOP, TRIS, INST>(sv, io, work, &ctr, thr);
     if (COUNT) {
         atomicAdd(&counters[0], (unsigned long long)ctr.nodes);
         atomicAdd(&counters[1], (unsigned long long)ctr.prims);
@@ -102,7 +102,10 @@ void trace_closest_dev(Scene &s, const float4 *rays, uint64_t n, float4 *hit_tuv
     if (!n) return;
     ClosestIO io{ rays, hit_tuvp, hit_inst, s.d_prims.ptr, (uint32_t)n };
     const bool tris = s.build_stats.n_spheres == 0; // the plain kernels drop the sphere branch; the counting ones keep it (same counts)
-    if (s.use_coop_prims()) launch_trace(s, tris ? k_trace_closest<false, true, true> : k_trace_closest<false, true>, k_trace_closest<true, true>, io, n);
+    if (s.n_blas > 0) { // two-level scene: the kernels that follow instance nodes
+        if (s.use_coop_prims()) launch_trace(s, k_trace_closest<false, true, false, true>, k_trace_closest<true, true, false, true>, io, n);
+        else launch_trace(s, k_trace_closest<false, false, false, true>, k_trace_closest<true, false, false, true>, io, n);
+    } else if (s.use_coop_prims()) launch_trace(s, tris ? k_trace_closest<false, true, true> : k_trace_closest<false, true>, k_trace_closest<true, true>, io, n);
     else launch_trace(s, tris ? k_trace_closest<false, false, true> : k_trace_closest<false, false>, k_trace_closest<true, false>, io, n);
 }
 void trace_any_dev(Scene &s, const float4 *rays, uint64_t n, uint32_t *occluded) {
@@ -110,7 +113,10 @@ void trace_any_dev(Scene &s, const float4 *rays, uint64_t n, uint32_t *occluded)
     if (!n) return;
     AnyIO io{ rays, occluded, (uint32_t)n };
     const bool tris = s.build_stats.n_spheres == 0;
-    if (s.use_coop_prims()) launch_trace(s, tris ? k_trace_any<false, true, true> : k_trace_any<false, true>, k_trace_any<true, true>, io, n);
+    if (s.n_blas > 0) {
+        if (s.use_coop_prims()) launch_trace(s, k_trace_any<false, true, false, true>, k_trace_any<true, true, false, true>, io, n);
+        else launch_trace(s, k_trace_any<false, false, false, true>, k_trace_any<true, false, false, true>, io, n);
+    } else if (s.use_coop_prims()) launch_trace(s, tris ? k_trace_any<false, true, true> : k_trace_any<false, true>, k_trace_any<true, true>, io, n);
     else launch_trace(s, tris ? k_trace_any<false, false, true> : k_trace_any<false, false>, k_trace_any<true, false>, io, n);
 }
 }// namespace pb2

@@ -19,9 +19,6 @@ namespace pb2 {
 #ifndef PB2_APPROX_IDIR
 #define PB2_APPROX_IDIR 1
 #endif
-#ifndef PB2_TRACE_PIPE
-#define PB2_TRACE_PIPE 0
-#endif
 #ifndef PB2_STACK_SIZE
 #define PB2_STACK_SIZE 32
 #endif
@@ -122,9 +119,10 @@ PB2_D bool intersect_prim(const SceneView &sv, uint32_t slot, float3 o, float3 d
 //   uint32_t size() const;
 //   uint32_t load(uint32_t i, float3 &o, float3 &d, float &tmin, float &tmax) const;   returns a token (e.g. the path slot)
 //        that is handed back to commit()
-//   void commit(bool valid, uint32_t token, const RayHit &h, bool hit);
+//   void commit(bool valid, uint32_t token, const RayHit &h, bool hit, uint32_t inst);
 //        called by ALL 32 lanes of the warp, converged, whenever at least one lane finished a ray
-//        (valid = this lane did), so implementations may use full-mask warp collectives
+//        (valid = this lane did), so implementations may use full-mask warp collectives.  inst: the instance of the hit when it
+//        lies in a bottom-level tree (two-level scenes), else ~0u = the instance id stored in the primitive record
 #ifndef PB2_REFILL_THRESHOLD
 #define PB2_REFILL_THRESHOLD 26
 #endif
@@ -138,9 +136,13 @@ struct RayState {
     uint32_t prim_base;
     uint32_t oct;
     int sp;
+    // two-level scenes only (INST): the instance whose bottom-level tree the ray is in (~0u at the top level) and the instance
+    // of the nearest hit so far (~0u: take it from the primitive record — top-level primitives carry their instance id)
+    uint32_t cur_inst, hit_inst;
 };
 
-PB2_D void ray_begin(RayState &r, float3 o, float3 d, float tmin, float tmax, bool empty_scene) {
+// reciprocal direction and octant of r.d (again after an instance transform)
+PB2_D void ray_set_dir(RayState &r, float3 d) {
 #if PB2_APPROX_IDIR
     // 1 / d feeds the slab tests only (never t, u, v), which are conservative by construction: the one-instruction hardware
     // reciprocal (<= 1 ulp) is enough, and kFar below carries the extra ulp.  ncu charged the three correctly rounded
@@ -153,12 +155,17 @@ PB2_D void ray_begin(RayState &r, float3 o, float3 d, float tmin, float tmax, bo
 #else
     auto safe_inv = [](float x) { return __frcp_rn(fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
 #endif
-    r.o = o, r.d = d, r.tmin = tmin;
+    r.d = d;
     r.idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     r.oct = (r.idir.x >= 0.f ? 4u : 0u) | (r.idir.y >= 0.f ? 2u : 0u) | (r.idir.z >= 0.f ? 1u : 0u);
+}
+PB2_D void ray_begin(RayState &r, float3 o, float3 d, float tmin, float tmax, bool empty_scene, uint32_t root = 0u) {
+    r.o = o, r.tmin = tmin;
+    ray_set_dir(r, d);
     r.hit.t = tmax, r.hit.u = r.hit.v = 0.f, r.hit.prim_slot = 0xffffffffu;
-    r.G = make_uint2(0u, empty_scene ? 0u : 0x80000000u);
+    r.G = make_uint2(root, empty_scene ? 0u : 0x80000000u);
     r.T = 0u, r.prim_base = 0u, r.sp = 0;
+    r.cur_inst = r.hit_inst = 0xffffffffu;
 }
 PB2_D bool ray_has_nodes(const RayState &r) { return (r.G.y & 0xff000000u) != 0u || r.sp > 0; }
 
@@ -183,29 +190,60 @@ struct TravStack {
         return sp < kSmemStack ? sm[sp * 128] : lo[sp - kSmemStack];
     }
 };
-struct NodeWords { // the five 128-bit words of a wide node, in registers between the fetch and the test
-    float4 n0;
-    uint4 n1, n2, n3, n4;
+// Two-level scenes (INST): a top-level child may be an INSTANCE NODE — an 80-byte slot in the node array whose exponent / mask
+// word is 0xffffffff (no real node has an exponent byte of 255), holding the root of a bottom-level tree (n1.x) and the
+// instance that places it in the world (n1.y).  Popping it takes the ray into that instance's object space: o' = M^-1 o,
+// d' = M^-1 d (not renormalised, so t keeps its meaning), a sentinel goes on the stack, and the world-space ray waits in shared
+// memory until the sentinel is popped again.  This is the reference's IAS -> GAS step (ias_manager.cpp:29-114): one tree per
+// shared mesh, any number of placements.
+constexpr uint32_t kInstanceNodeTag = 0xffffffffu, kStackSentinel = 0xffffffffu;
+struct WorldRay { // this lane's column of the saved world-space rays (stride: CTA size)
+    float *p;
+    PB2_D void save(float3 o, float3 d) const { p[0] = o.x, p[128] = o.y, p[256] = o.z, p[384] = d.x, p[512] = d.y, p[640] = d.z; }
+    PB2_D void load(float3 &o, float3 &d) const { o = mk3(p[0], p[128], p[256]), d = mk3(p[384], p[512], p[640]); }
 };
-// pops the nearest pending internal node of the ray and requests its five words; the siblings that remain go (back) to the stack
-PB2_D void node_pop_fetch(const SceneView &sv, RayState &r, const TravStack &stack, NodeWords &w) {
-    if (!(r.G.y & 0xff000000u)) r.G = stack.pop(r.sp);
+// pops the nearest pending internal node, tests its eight children, leaves the hit children in G / T; returns false when no
+// wide node was tested (INST: the pop ended a bottom-level tree with nothing left above it, or entered one)
+template<bool INST = false>
+PB2_D bool node_step(const SceneView &sv, RayState &r, const TravStack &stack, const WorldRay &world = WorldRay{ nullptr }) {
+    if (!(r.G.y & 0xff000000u)) {
+        r.G = stack.pop(r.sp);
+        if (INST && r.G.x == kStackSentinel) { // the bottom-level tree is exhausted: back to the world-space ray
+            float3 o, d;
+            world.load(o, d);
+            r.o = o;
+            ray_set_dir(r, d);
+            r.cur_inst = 0xffffffffu;
+            r.G.y = 0u, r.T = 0u;
+            if (r.sp <= 0) return false;
+            r.G = stack.pop(r.sp);
+        }
+    }
     const uint32_t bit = 31u - __clz(r.G.y);
     r.G.y &= ~(1u << bit);
     const uint32_t slot = (bit - 24u) ^ r.oct;
     const uint32_t rel = __popc(r.G.y & 0xffu & ((1u << slot) - 1u));
     const Bvh8Node *np = sv.nodes + (r.G.x + rel);
     if (r.G.y & 0xff000000u) stack.push(r.sp, r.G);
-    w.n0 = __ldg(&np->n0);
-    w.n1 = __ldg(&np->n1), w.n2 = __ldg(&np->n2), w.n3 = __ldg(&np->n3), w.n4 = __ldg(&np->n4);
-}
-// tests the eight children of a fetched node, leaves the hit children in G / T
-PB2_D void node_test(RayState &r, const NodeWords &w) {
-    const float4 n0 = w.n0;
-    const uint4 n1 = w.n1, n2 = w.n2, n3 = w.n3, n4 = w.n4;
+
+    const float4 n0 = __ldg(&np->n0);
+    const uint4 n1 = __ldg(&np->n1);
+    const uint32_t ebits = __float_as_uint(n0.w);
+    if (INST && ebits == kInstanceNodeTag) {
+        const DevInstance *in = sv.instances + n1.y;
+        const float4 r0 = __ldg(&in->inv[0]), r1 = __ldg(&in->inv[1]), r2 = __ldg(&in->inv[2]);
+        world.save(r.o, r.d);
+        r.o = ix_point(r0, r1, r2, r.o);
+        ray_set_dir(r, ix_vector(r0, r1, r2, r.d));
+        r.cur_inst = n1.y;
+        stack.push(r.sp, make_uint2(kStackSentinel, 0u));
+        r.G = make_uint2(n1.x, 0x80000000u);
+        r.T = 0u;
+        return false;
+    }
+    const uint4 n2 = __ldg(&np->n2), n3 = __ldg(&np->n3), n4 = __ldg(&np->n4);
     const bool px = r.idir.x >= 0.f, py = r.idir.y >= 0.f, pz = r.idir.z >= 0.f;
     const uint32_t oct4 = r.oct * 0x01010101u;
-    const uint32_t ebits = __float_as_uint(n0.w);
     const float sx = __uint_as_float((ebits & 0xffu) << 23), sy = __uint_as_float(((ebits >> 8) & 0xffu) << 23),
                 sz = __uint_as_float(((ebits >> 16) & 0xffu) << 23);
     const float3 adj = mk3(sx * r.idir.x, sy * r.idir.y, sz * r.idir.z);
@@ -238,11 +276,7 @@ PB2_D void node_test(RayState &r, const NodeWords &w) {
     r.G = make_uint2(n1.x, (hitmask & 0xff000000u) | (ebits >> 24));
     r.T = hitmask & 0x00ffffffu;
     r.prim_base = n1.y;
-}
-PB2_D void node_step(const SceneView &sv, RayState &r, const TravStack &stack) {
-    NodeWords w;
-    node_pop_fetch(sv, r, stack, w);
-    node_test(r, w);
+    return true;
 }
 
 // resident 128-thread CTAs per SM the trace kernels are compiled for: 9 (56 registers) with the per-lane primitive loop,
@@ -268,137 +302,12 @@ struct CoopShared {                // per warp
 // (profiles/README.md): +7 % / +10 % Mrays/s for incoherent closest-hit / any-hit rays on the 30 M-triangle terrain, where
 // few lanes reach a leaf per step; -17 % on the 36-triangle Cornell box, where every lane does and the bookkeeping only
 // adds instructions.  The host picks per scene (Scene::coop_prims).
-// Pipelined form of the cooperative loop below.  ncu (30 M-triangle terrain, incoherent rays, profiles/r2b_c4_ncu.md): 41 % of
-// the stall samples wait on the long scoreboard, in two places per iteration — the first use of the node words and the first
-// use of the primitive words — one after the other.  Here the NEXT node of every lane is popped and requested right after the
-// current node's test, before the primitive phase: its latency passes behind the primitive fetch and tests, and the warp waits
-// once per iteration instead of twice.  The node words live in registers across the primitive phase (more registers per thread:
-// PB2_TRACE_MINB_PIPE resident CTAs).  Same node and primitive tests in the same order per ray; a ray's primitives are still
-// tested before its next node (hit.t is current when the prefetched node is tested).
-template<bool ANY, bool COUNT, bool TRIS, class IO>
-PB2_D void trace_persistent_pipe(const SceneView &sv, IO &io, uint32_t *__restrict__ work_counter, TraceCounters *ctr, int refill_threshold) {
-    constexpr uint32_t kFull = 0xffffffffu;
-    __shared__ CoopShared s_coop[kTraceWarps];
-    CoopShared &sm = s_coop[threadIdx.x >> 5];
-    const uint32_t n = io.size();
-    const uint32_t lane = threadIdx.x & 31u;
-    __shared__ uint2 s_stack[(kSmemStack > 0 ? kSmemStack : 1) * 128];
-    uint2 stack_local[PB2_STACK_SIZE - kSmemStack];
-    const TravStack stack{ s_stack + threadIdx.x, stack_local };
-    RayState r;
-    NodeWords w;
-    r.T = 0u, r.G = make_uint2(0u, 0u), r.sp = 0;
-    uint32_t ray = 0;
-    bool busy = false, fetched = false; // fetched: w holds a node of this lane's ray that has not been tested yet
-    bool exhausted = false;
-    for (;;) {
-        const uint32_t busy_mask = __ballot_sync(kFull, busy);
-        if (!exhausted && __popc(busy_mask) < refill_threshold) {
-            const uint32_t idle = ~busy_mask;
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(work_counter, (uint32_t)__popc(idle));
-            base = __shfl_sync(kFull, base, 0);
-            const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
-            if (!busy && mine < n) {
-                float3 o, d;
-                float tmin, tmax;
-                ray = io.load(mine, o, d, tmin, tmax);
-                ray_begin(r, o, d, tmin, tmax, sv.n_nodes == 0);
-                busy = true;
-                if (ray_has_nodes(r)) { // the root: nothing to hide this fetch behind
-                    node_pop_fetch(sv, r, stack, w);
-                    r.G.y &= 0x00ffffffu;
-                    fetched = true;
-                }
-            }
-            exhausted = base + __popc(idle) >= n;
-        } else if (busy_mask == 0u) {
-            break;
-        }
-        // ---- test the node requested one iteration ago, then request the next one ----
-        if (fetched) {
-            node_test(r, w);
-            fetched = false;
-            if (COUNT) ++ctr->nodes;
-        }
-        if (busy && ray_has_nodes(r)) {
-            // the group left by the test stays in r.G for the NEXT pop; node_pop_fetch consumes one node of it and pushes the rest
-            node_pop_fetch(sv, r, stack, w);
-            r.G.y &= 0x00ffffffu; // what remains of the group is on the stack now
-            fetched = true;
-        }
-        // ---- primitives of the node just tested, warp-cooperatively (as in trace_persistent) ----
-        for (;;) {
-            const uint32_t T = busy ? r.T : 0u;
-            if (!__any_sync(kFull, T != 0u)) break;
-            const uint32_t cnt = min((uint32_t)__popc(T), (uint32_t)kPairsPerLane);
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int dlt = 1; dlt < 32; dlt <<= 1) {
-                const uint32_t up = __shfl_up_sync(kFull, incl, dlt);
-                if ((int)lane >= dlt) incl += up;
-            }
-            const uint32_t total = __shfl_sync(kFull, incl, 31), excl = incl - cnt;
-            sm.o[lane] = make_float4(r.o.x, r.o.y, r.o.z, r.tmin);
-            sm.d[lane] = make_float4(r.d.x, r.d.y, r.d.z, r.hit.t);
-            sm.base[lane] = r.prim_base;
-            sm.best[lane] = ~0ull;
-            {
-                uint32_t tt = T;
-                for (uint32_t j = 0; j < cnt; ++j) {
-                    const uint32_t b = __ffs(tt) - 1;
-                    tt &= tt - 1;
-                    sm.pairs[excl + j] = (uint16_t)((lane << 5) | b);
-                }
-                if (busy) r.T = tt;
-            }
-            __syncwarp();
-            for (uint32_t c = 0; c < total; c += 32u) {
-                const uint32_t k = c + lane;
-                RayHit h;
-                h.t = 0.f, h.u = 0.f, h.v = 0.f, h.prim_slot = 0xffffffffu;
-                if (k < total) {
-                    const uint32_t e = sm.pairs[k], own = e >> 5;
-                    if (!ANY || sm.best[own] == ~0ull) {
-                        const float4 ro = sm.o[own], rd = sm.d[own];
-                        h.t = rd.w;
-                        if (COUNT) ++ctr->prims;
-                        if (intersect_prim<true, TRIS>(sv, sm.base[own] + (e & 31u), mk3(ro), mk3(rd), ro.w, h))
-                            atomicMin(&sm.best[own], ((unsigned long long)__float_as_uint(h.t) << 32) | k);
-                    }
-                }
-                __syncwarp();
-                const unsigned long long b = sm.best[lane];
-                const uint32_t bk = (uint32_t)b;
-                const bool won = busy && b != ~0ull && bk >= c && bk < c + 32u;
-                const uint32_t src = won ? bk - c : lane;
-                const float wt = __shfl_sync(kFull, h.t, src), wu = __shfl_sync(kFull, h.u, src), wv = __shfl_sync(kFull, h.v, src);
-                const uint32_t ws = __shfl_sync(kFull, h.prim_slot, src);
-                if (won) {
-                    r.hit.t = wt, r.hit.u = wu, r.hit.v = wv, r.hit.prim_slot = ws;
-                    if (ANY) r.T = 0u, r.G.y = 0u, r.sp = 0, fetched = false; // occluded: the prefetched node is dropped
-                }
-            }
-            __syncwarp();
-        }
-        __syncwarp();
-        const bool done = busy && !fetched && !ray_has_nodes(r);
-        if (__any_sync(kFull, done)) {
-            io.commit(done, ray, r.hit, r.hit.prim_slot != 0xffffffffu);
-            if (done) busy = false;
-        }
-    }
-}
-
-template<bool ANY, bool COUNT, bool COOP, bool TRIS, class IO>
+// INST: the scene has bottom-level trees behind instance nodes (Scene::n_blas > 0); compiled out otherwise.
+template<bool ANY, bool COUNT, bool COOP, bool TRIS, bool INST = false, class IO>
 PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ work_counter, TraceCounters *ctr, int refill_threshold = PB2_REFILL_THRESHOLD) {
-#if PB2_TRACE_PIPE
-    if (COOP) {
-        trace_persistent_pipe<ANY, COUNT, TRIS>(sv, io, work_counter, ctr, refill_threshold);
-        return;
-    }
-#endif
     constexpr uint32_t kFull = 0xffffffffu;
+    __shared__ float s_world[INST ? 6 * 128 : 1];
+    const WorldRay world{ s_world + (INST ? threadIdx.x : 0) };
     __shared__ CoopShared s_coop[COOP ? kTraceWarps : 1];
     CoopShared &sm = s_coop[COOP ? threadIdx.x >> 5 : 0];
     const uint32_t n = io.size();
@@ -424,7 +333,7 @@ PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ 
                 float3 o, d;
                 float tmin, tmax;
                 ray = io.load(mine, o, d, tmin, tmax);
-                ray_begin(r, o, d, tmin, tmax, sv.n_nodes == 0);
+                ray_begin(r, o, d, tmin, tmax, sv.n_nodes == 0, sv.root);
                 busy = true;
             }
             exhausted = base + __popc(idle) >= n;
@@ -433,13 +342,14 @@ PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ 
         }
         // ---- one node step, then the primitives it uncovered ----
         if (busy && ray_has_nodes(r)) {
-            node_step(sv, r, stack);
-            if (COUNT) ++ctr->nodes;
+            const bool tested = node_step<INST>(sv, r, stack, world);
+            if (COUNT && tested) ++ctr->nodes;
             while (!COOP && r.T) {
                 const uint32_t i = __ffs(r.T) - 1;
                 r.T &= r.T - 1;
                 if (COUNT) ++ctr->prims;
                 if (intersect_prim<false, TRIS>(sv, r.prim_base + i, r.o, r.d, r.tmin, r.hit)) {
+                    if (INST) r.hit_inst = r.cur_inst;
                     if (ANY) r.T = 0u, r.G.y = 0u, r.sp = 0;
                 }
             }
@@ -499,6 +409,7 @@ PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ 
                 const uint32_t ws = __shfl_sync(kFull, h.prim_slot, src);
                 if (won) {
                     r.hit.t = wt, r.hit.u = wu, r.hit.v = wv, r.hit.prim_slot = ws;
+                    if (INST) r.hit_inst = r.cur_inst; // the pairs of this round belong to the tree the owner is in right now
                     if (ANY) r.T = 0u, r.G.y = 0u, r.sp = 0;
                 }
             }
@@ -507,7 +418,7 @@ PB2_D void trace_persistent(const SceneView &sv, IO &io, uint32_t *__restrict__ 
         __syncwarp();
         const bool done = busy && !ray_has_nodes(r);
         if (__any_sync(kFull, done)) {
-            io.commit(done, ray, r.hit, r.hit.prim_slot != 0xffffffffu);
+            io.commit(done, ray, r.hit, r.hit.prim_slot != 0xffffffffu, INST ? r.hit_inst : 0xffffffffu);
             if (done) busy = false;
         }
     }

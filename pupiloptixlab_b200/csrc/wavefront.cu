@@ -184,7 +184,7 @@ struct ExtendIO {
         return p;
     }
     // writes the hit record and appends the path to the queue of the hit material type (0 = miss)
-    PB2_D void commit(bool valid, uint32_t p, const RayHit &h, bool hit) const {
+    PB2_D void commit(bool valid, uint32_t p, const RayHit &h, bool hit, uint32_t inst_of_hit) const {
         uint32_t type = 0;
         if (valid) {
             int32_t inst = -1;
@@ -193,7 +193,7 @@ struct ExtendIO {
             if (hit) {
                 const float4 *rec = reinterpret_cast<const float4 *>(sv.prims + h.prim_slot);
                 prim = __float_as_uint(__ldg(rec).w);
-                inst = (int32_t)__float_as_uint(__ldg(rec + 1).w);
+                inst = inst_of_hit != 0xffffffffu ? (int32_t)inst_of_hit : (int32_t)__float_as_uint(__ldg(rec + 1).w);
                 sphere = __float_as_uint(__ldg(rec + 2).w) != 0u;
                 type = (uint32_t)__ldg(&sv.instances[inst].mat_type) & 7u;
             }
@@ -216,7 +216,7 @@ struct ShadowIO {
         o = mk3(ro), d = mk3(rd), tmin = kShadowTmin, tmax = ro.w;
         return i;
     }
-    PB2_D void commit(bool valid, uint32_t i, const RayHit &, bool hit) const {
+    PB2_D void commit(bool valid, uint32_t i, const RayHit &, bool hit, uint32_t) const {
         if (valid && !hit) { // main.cu:127 `if (!occluded)`
             const uint32_t p = __float_as_uint(pa.shq[3 * (size_t)i + 1].w);
             const float4 c = pa.shq[3 * (size_t)i + 2];
@@ -228,24 +228,24 @@ struct ShadowIO {
     }
 };
 
-template<bool COUNT, bool COOP, bool TRIS = false>
+template<bool COUNT, bool COOP, bool TRIS = false, bool INST = false>
 __global__ void __launch_bounds__(128, PB2_TRACE_MINB(COOP)) k_extend(SceneView sv, PathArrays pa, const uint32_t *__restrict__ q_in, const uint32_t *__restrict__ n_in,
                                                 uint32_t *__restrict__ q_mat, uint32_t *__restrict__ mat_counts, uint32_t capacity, int sort,
                                                 uint32_t *__restrict__ work, unsigned long long *__restrict__ trav, int refill) {
     ExtendIO io{ sv, pa, q_in, q_mat, mat_counts, *n_in, capacity, sort };
     TraceCounters ctr{ 0, 0 };
-    trace_persistent<false, COUNT, COOP, TRIS>(sv, io, work, &ctr, refill);
+    trace_persistent<false, COUNT, COOP, TRIS, INST>(sv, io, work, &ctr, refill);
     if (COUNT) {
         atomicAdd(&trav[0], (unsigned long long)ctr.nodes);
         atomicAdd(&trav[1], (unsigned long long)ctr.prims);
     }
 }
-template<bool COUNT, bool COOP, bool TRIS = false>
+template<bool COUNT, bool COOP, bool TRIS = false, bool INST = false>
 __global__ void __launch_bounds__(128, PB2_TRACE_MINB(COOP)) k_shadow(SceneView sv, PathArrays pa, const uint32_t *__restrict__ n_in, uint32_t *__restrict__ work,
                                                 unsigned long long *__restrict__ trav, int refill) {
     ShadowIO io{ pa, *n_in, COUNT ? trav + 4 : nullptr };
     TraceCounters ctr{ 0, 0 };
-    trace_persistent<true, COUNT, COOP, TRIS>(sv, io, work, &ctr, refill);
+    trace_persistent<true, COUNT, COOP, TRIS, INST>(sv, io, work, &ctr, refill);
     if (COUNT) {
         atomicAdd(&trav[2], (unsigned long long)ctr.nodes);
         atomicAdd(&trav[3], (unsigned long long)ctr.prims);
@@ -677,6 +677,7 @@ void render(Scene &s, const pb2_launch_params &lp) {
     const SceneView sv = s.view();
     const bool coop = s.use_coop_prims();
     const bool tris = s.build_stats.n_spheres == 0; // no analytic spheres: the trace kernels without the sphere branch
+    const bool inst = s.n_blas > 0;                  // two-level scene: the trace kernels that follow instance nodes
     // material sorting pays when shading diverges: on by default only for scenes with more than one material type
     const bool sorted = s.sort_by_material == 1 || (s.sort_by_material < 0 && s.n_material_types > 1);
     wf.sorted = sorted, wf.lanes_used = n_lanes;
@@ -735,8 +736,11 @@ void render(Scene &s, const pb2_launch_params &lp) {
             uint32_t *q_in = ln.q_ext[r & 1].ptr, *q_out = ln.q_ext[(r + 1) & 1].ptr;
             stage_begin(1);
             {
-                auto k = s.counting ? (coop ? k_extend<true, true> : k_extend<true, false>)
-                                    : tris ? (coop ? k_extend<false, true, true> : k_extend<false, false, true>) : (coop ? k_extend<false, true> : k_extend<false, false>);
+                auto k = inst ? (s.counting ? (coop ? k_extend<true, true, false, true> : k_extend<true, false, false, true>)
+                                            : (coop ? k_extend<false, true, false, true> : k_extend<false, false, false, true>))
+                         : s.counting ? (coop ? k_extend<true, true> : k_extend<true, false>)
+                         : tris       ? (coop ? k_extend<false, true, true> : k_extend<false, false, true>)
+                                      : (coop ? k_extend<false, true> : k_extend<false, false>);
                 k<<<grid_trace, 128, 0, st>>>(sv, pa, q_in, ctr + CTR_EXT, ln.q_mat.ptr, ctr + CTR_MAT0, (uint32_t)ln.capacity, sorted ? 1 : 0,
                                               ctr + CTR_WORK_EXT, s.counting ? wf.trav_counters.ptr : nullptr, s.refill_threshold);
             }
@@ -801,8 +805,11 @@ void render(Scene &s, const pb2_launch_params &lp) {
             wf.launches += 1 + shade_launches, ++wf.n_extend, ++wf.n_shade;
             if (r + 1 < rounds) { // the last round cannot emit rays (depth >= max_depth)
                 stage_begin(3);
-                auto k = s.counting ? (coop ? k_shadow<true, true> : k_shadow<true, false>)
-                                    : tris ? (coop ? k_shadow<false, true, true> : k_shadow<false, false, true>) : (coop ? k_shadow<false, true> : k_shadow<false, false>);
+                auto k = inst ? (s.counting ? (coop ? k_shadow<true, true, false, true> : k_shadow<true, false, false, true>)
+                                            : (coop ? k_shadow<false, true, false, true> : k_shadow<false, false, false, true>))
+                         : s.counting ? (coop ? k_shadow<true, true> : k_shadow<true, false>)
+                         : tris       ? (coop ? k_shadow<false, true, true> : k_shadow<false, false, true>)
+                                      : (coop ? k_shadow<false, true> : k_shadow<false, false>);
                 k<<<grid_trace, 128, 0, st>>>(sv, pa, ctr + CTR_SHADOW, ctr + CTR_WORK_SHADOW, s.counting ? wf.trav_counters.ptr : nullptr, s.refill_threshold);
                 PB2_LAUNCH_CHECK();
                 stage_end();

@@ -285,6 +285,11 @@ int pupil_set_bvh_builder(int builder) {
     W()->SetBvhBuilder(builder);
     return 0;
 }
+int pupil_set_instancing(int mode) {
+    if (!Ready()) return Fail("pupil_init first");
+    W()->SetInstancing(mode);
+    return 0;
+}
 int pupil_build_stats(pb2_build_stats *stats) {
     if (!Ready() || !stats) return Fail("no scene");
     W()->GetSceneHandle();

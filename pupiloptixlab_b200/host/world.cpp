@@ -368,7 +368,18 @@ void World::Init() noexcept {
                     emitters->ComputeProbability();
                 }
             }
-            m_geometry_dirty = true;
+            // IASManager::UpdateInstance + IAS::Update (ias_manager.cpp:116-151): the new transform goes to the device scene and
+            // only the top level of the acceleration structure is rebuilt; bottom-level trees stay
+            bool incremental = false;
+            if (m_pb2 && !m_geometry_dirty) {
+                for (size_t k = 0; k < m_ros.size(); ++k)
+                    if (m_ros[k].get() == ro) {
+                        incremental = pb2_scene_set_instance_transform(m_pb2, (uint32_t)k, ro->transform.matrix.e) == PB2_OK;
+                        break;
+                    }
+            }
+            if (incremental) m_transform_dirty = true;
+            else m_geometry_dirty = true;
             EventDispatcher<EWorldEvent::RenderInstanceUpdate>(p);
         });
     }
@@ -432,6 +443,7 @@ bool World::LoadScene(resource::Scene *s) noexcept {
 }
 
 void World::SetBvhBuilder(int builder) noexcept { m_builder = builder, m_geometry_dirty = true; }
+void World::SetInstancing(int mode) noexcept { m_instancing = mode, m_geometry_dirty = true; }
 
 // IASManager::SetInstance + GAS/IAS builds, replaced: every render object becomes one pb2 instance.  Meshes
 // are uploaded once per shape; the emitter offset of an instance is the running sum of sub_emitters_num over
@@ -442,6 +454,7 @@ void World::RebuildDeviceScene() noexcept {
     Pb2Check(pb2_scene_clear(m_pb2), "pb2_scene_clear");
     emitters->Invalidate(); // pb2_scene_clear drops the emitter table with the geometry
     if (m_builder >= 0) Pb2Check(pb2_scene_set_builder(m_pb2, m_builder), "pb2_scene_set_builder");
+    if (m_instancing >= 0) Pb2Check(pb2_scene_set_option(m_pb2, "instancing", m_instancing), "pb2_scene_set_option(instancing)");
     std::unordered_map<uint32_t, uint32_t> mesh_of_shape;
     for (auto &ro : m_ros) {
         uint32_t mesh_id = PB2_MESH_SPHERE;
@@ -466,10 +479,14 @@ void World::RebuildDeviceScene() noexcept {
         Pb2Check(pb2_scene_add_instance(m_pb2, mesh_id, ro->transform.matrix.e, flags, &ro->mat, offset, nullptr), "pb2_scene_add_instance");
     }
     Pb2Check(pb2_bvh_build(m_pb2, &m_build_stats), "pb2_bvh_build");
-    m_geometry_dirty = false;
+    m_geometry_dirty = false, m_transform_dirty = false;
 }
 pb2_scene *World::GetSceneHandle() noexcept {
     if (m_geometry_dirty || !m_pb2) RebuildDeviceScene();
+    else if (m_transform_dirty) {
+        Pb2Check(pb2_bvh_build(m_pb2, &m_build_stats), "pb2_bvh_build (top level)");
+        m_transform_dirty = false;
+    }
     camera->Upload(m_pb2);
     emitters->Upload(m_pb2);
     return m_pb2;

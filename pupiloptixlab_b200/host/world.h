@@ -125,8 +125,11 @@ public:
     // emitter table.  Rebuilds the BVH when instances changed.
     pb2_scene *GetSceneHandle() noexcept;
     const pb2_build_stats &GetBuildStats() const noexcept { return m_build_stats; }
-    // 0 = LBVH, 1 = binned SAH (pb2_scene_set_builder); applies to the next build
+    // 0 = LBVH, 1 = binned SAH along the Morton order, 2 = SAH-driven clustering (pb2_scene_set_builder); applies to the next build
     void SetBvhBuilder(int builder) noexcept;
+    // which shapes get a bottom-level tree shared by their render objects, as GASManager::RefGAS does for every shape
+    // (gas_manager.cpp:10): 0 none, 1 shapes used more than once (default), 2 every mesh; applies to the next build
+    void SetInstancing(int mode) noexcept;
 
     RenderObject *GetRenderObject(std::string_view name) const noexcept;
     RenderObject *GetRenderObject(size_t index) const noexcept;
@@ -149,7 +152,8 @@ private:
     pb2_scene *m_pb2 = nullptr;
     pb2_build_stats m_build_stats{};
     bool m_geometry_dirty = true;
-    int m_builder = -1;
+    bool m_transform_dirty = false; // only object transforms changed since the last build: the top level is rebuilt, nothing else
+    int m_builder = -1, m_instancing = -1;
 };
 }// namespace world
 }// namespace Pupil

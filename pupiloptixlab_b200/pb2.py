@@ -59,7 +59,7 @@ class LaunchParams(C.Structure):
 
 class BuildStats(C.Structure):
     _fields_ = [("n_prims", u64), ("n_triangles", u64), ("n_spheres", u64), ("n_nodes", u64), ("bvh_bytes", u64),
-                ("build_ms", f32), ("sah_cost", f32), ("max_depth", u32)]
+                ("build_ms", f32), ("sah_cost", f32), ("max_depth", u32), ("n_blas", u32), ("n_instance_leaves", u64), ("top_level_ms", f32), ("pad0", u32)]
 
 
 class RenderStats(C.Structure):
@@ -93,7 +93,7 @@ def lib():
             "pb2_scene_clear": [vp], "pb2_scene_set_stream": [vp, vp],
             "pb2_scene_add_mesh": [vp, vp, vp, vp, vp, u32, u32, P(u32)],
             "pb2_scene_add_instance": [vp, u32, P(f32), u32, P(Material), i32, P(u32)],
-            "pb2_scene_set_emitters": [vp, P(Emitter), u32, P(Emitter)], "pb2_scene_set_camera": [vp, P(f32), P(f32)],
+            "pb2_scene_set_emitters": [vp, P(Emitter), u32, P(Emitter)], "pb2_scene_set_instance_transform": [vp, u32, P(f32)], "pb2_scene_set_camera": [vp, P(f32), P(f32)],
             "pb2_bvh_build": [vp, P(BuildStats)], "pb2_scene_set_builder": [vp, C.c_int],
             "pb2_trace_closest": [vp, vp, u64, vp], "pb2_trace_any": [vp, vp, u64, vp],
             "pb2_trace_closest_dev": [vp, vp, u64, vp, vp], "pb2_trace_any_dev": [vp, vp, u64, vp],
@@ -216,6 +216,11 @@ class Scene:
         check(lib().pb2_scene_add_instance(self.h, mesh_id, x.ctypes.data_as(C.POINTER(f32)), flags,
                                             C.byref(material) if material is not None else None, emitter_offset, C.byref(iid)))
         return iid.value
+
+    def set_instance_transform(self, instance_id: int, xform):
+        """new 3x4 (or 4x4) object->world transform; the next build() keeps the bottom-level trees"""
+        m = np.ascontiguousarray(np.asarray(xform, np.float32).reshape(-1)[:12])
+        check(lib().pb2_scene_set_instance_transform(self.h, instance_id, m.ctypes.data_as(C.POINTER(f32))))
 
     def set_emitters(self, areas: list, env: Emitter | None = None):
         arr = (Emitter * max(1, len(areas)))(*areas)

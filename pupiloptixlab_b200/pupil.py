@@ -50,7 +50,7 @@ def lib():
             "pupil_buffer_download": [C.c_char_p, vp, u64], "pupil_buffer_upload": [C.c_char_p, vp, u64],
             "pupil_get_film": [P(u32), P(u32), P(u32)], "pupil_get_camera": [P(f32), P(f32), P(f32)], "pupil_num_instances": [],
             "pupil_get_instance": [u32, P(f32), P(pb2.Material), P(i32), P(u32), P(u32), P(i32)], "pupil_num_area_emitters": [],
-            "pupil_get_emitters": [P(pb2.Emitter), P(pb2.Emitter), P(i32)], "pupil_scene_handle": [P(vp)], "pupil_set_bvh_builder": [C.c_int],
+            "pupil_get_emitters": [P(pb2.Emitter), P(pb2.Emitter), P(i32)], "pupil_scene_handle": [P(vp)], "pupil_set_bvh_builder": [C.c_int], "pupil_set_instancing": [C.c_int],
             "pupil_build_stats": [P(pb2.BuildStats)], "pupil_render_stats": [P(pb2.RenderStats)], "pupil_camera_move": [f32, f32, f32],
             "pupil_camera_rotate": [f32, f32], "pupil_camera_set_fov": [f32],
             "pupil_register_image": [C.c_char_p, vp, u32, u32], "pupil_image_load": [C.c_char_p, P(u32), P(u32), vp, u64],
@@ -105,9 +105,12 @@ def load_scene(desc: SceneDesc, host_only: bool = False, borrow: bool = True):
     alive until the next scene is loaded.  Arrays that live in pinned memory (e.g. numpy views of pinned torch tensors) make
     the upload a straight DMA."""
     global _mesh_serial, _borrowed
-    names, keep = {}, {}
+    names, keep, by_mesh = {}, {}, {}
     for i, sh in enumerate(desc.shapes):
         if sh.type != "obj":
+            continue
+        if id(sh.mesh) in by_mesh:  # shapes that share a mesh share ONE registered shape: the device holds it once (bottom-level tree + instances)
+            names[i] = by_mesh[id(sh.mesh)]
             continue
         _mesh_serial += 1
         key = f"mem:{desc.name}_{i}_{_mesh_serial}"
@@ -118,7 +121,7 @@ def load_scene(desc: SceneDesc, host_only: bool = False, borrow: bool = True):
         T = None if m.get("texcoords") is None else np.ascontiguousarray(m["texcoords"], np.float32)
         fn = lib().pupil_register_mesh_borrowed if borrow else lib().pupil_register_mesh
         check(fn(key.encode(), pb2._ptr(P), pb2._ptr(N), pb2._ptr(T), pb2._ptr(I), P.shape[0], I.shape[0]))
-        names[i] = key
+        names[i] = by_mesh[id(sh.mesh)] = key
         if borrow:
             keep[key] = (P, I, N, T)
     from . import scenes as _scenes
@@ -297,6 +300,10 @@ def scene_handle() -> pb2.Scene:
 
 def set_bvh_builder(builder: int):
     check(lib().pupil_set_bvh_builder(builder))
+
+
+def set_instancing(mode: int):
+    check(lib().pupil_set_instancing(mode))
 
 
 def build_stats() -> pb2.BuildStats:
