@@ -172,7 +172,7 @@ def test_degenerate_slivers_and_transformed_spheres_at_scale(port_lib):
     ref, _ = osc.trace_closest(rays[sel], threads=os.cpu_count())
     ties = compare_hits(gpu[sel], ref, rays[sel])
     assert ties <= 40
-    assert np.count_nonzero(ref["inst"] >= 1) > 100  # spheres are hit too
+    assert np.count_nonzero(ref["inst"] >= 1) > 20  # spheres are hit too (the dense soup hides most of them)
     # the oracle's BVH itself against its exhaustive loop on a subset
     sub = sel[:384]
     brute, _ = osc.trace_closest(rays[sub], brute=True, threads=os.cpu_count())
