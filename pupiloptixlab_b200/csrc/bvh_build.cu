@@ -8,14 +8,13 @@
 //
 // Stages (all on the scene's stream):
 //   1 emit_prims      instance triangles / spheres -> 48 B world-space records + AABBs + scene bounds
-//   2 morton + sort   63-bit keys, cub::DeviceRadixSort::SortPairs
+//   2 morton + sort   63-bit keys, in-tree onesweep radix sort (radix_sort.cu)
 //   3 radix_tree      Karras 2012 binary radix tree (ties broken by index)
 //   4 refit           bottom-up AABBs with per-node arrival counters
 //   5 collapse        breadth-first: binary subtree -> up to 8 children by largest-area expansion,
 //                     octant slot assignment, quantisation, leaf primitive copy
 #include "scene.cuh"
 #include "traverse.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
 
 namespace pb2 {
@@ -482,6 +481,8 @@ __global__ void __launch_bounds__(128, PB2_COLLAPSE_MINB) k_collapse(CollapseCtx
 // bvh_ploc.cu: SAH-driven bottom-up clustering producing the same BinTree arrays; returns the root's node index
 int build_binary_ploc(cudaStream_t st, uint32_t n, const float4 *box_lo, const float4 *box_hi, const uint32_t *sorted, int *left, int *right, int2 *range,
                       float4 *lo, float4 *hi, int radius, uint32_t *rounds_out);
+// radix_sort.cu: in-tree onesweep sort of (64-bit key, 32-bit value) pairs; true = the result is in the alt buffers
+bool radix_sort_pairs(cudaStream_t st, uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt, uint32_t n, int begin_bit, int end_bit);
 // bvh_sah.cu: binned-SAH binary tree producing the same BinTree arrays + `sorted` permutation
 bool sah_builder_available();
 void build_binary_sah(cudaStream_t st, uint32_t n, const float4 *box_lo, const float4 *box_hi, const uint32_t *sorted, int *left, int *right, int2 *range,
@@ -535,14 +536,16 @@ void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, 
     BinTree t{ left.ptr, right.ptr, parent.ptr, range.ptr, nlo.ptr, nhi.ptr, n };
     int root_ref = 0; // binary node the collapse starts from (node 0 for the top-down builders)
     {
+        // 63-bit Morton keys, sorted by the in-tree onesweep radix sort (radix_sort.cu: eight 8-bit passes; measured against
+        // cub::DeviceRadixSort on the 30 M-triangle terrain: 380 vs 347 us per pass, the whole build 12.9 vs 12.8 ms)
         DevBuf<uint64_t> keys(n), keys_sorted(n);
         DevBuf<uint32_t> vals(n);
-        k_morton<<<div_up(n, 256), 256, 0, st>>>(box_lo.ptr, box_hi.ptr, bounds.ptr, n, keys.ptr, vals.ptr);
+        k_morton<<<div_up(n, 256), 256, 0, st>>>(box_lo.ptr, box_hi.ptr, bounds.ptr, n, keys_sorted.ptr, sorted.ptr);
         PB2_LAUNCH_CHECK();
-        size_t tmp_bytes = 0;
-        PB2_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys.ptr, keys_sorted.ptr, vals.ptr, sorted.ptr, (int)n, 0, 63, st));
-        DevBuf<uint8_t> tmp(tmp_bytes);
-        PB2_CUDA(cub::DeviceRadixSort::SortPairs(tmp.ptr, tmp_bytes, keys.ptr, keys_sorted.ptr, vals.ptr, sorted.ptr, (int)n, 0, 63, st));
+        if (radix_sort_pairs(st, keys_sorted.ptr, keys.ptr, sorted.ptr, vals.ptr, n, 0, 63)) { // an odd pass count leaves the result in the scratch buffers
+            PB2_CUDA(cudaMemcpyAsync(keys_sorted.ptr, keys.ptr, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+            PB2_CUDA(cudaMemcpyAsync(sorted.ptr, vals.ptr, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        }
         // a top level with instance leaves needs the weighted counts of k_refit: it always takes the LBVH path (it is small)
         if (n > 1 && s.builder == 2 && !inst_leaves) {
             // bottom-up clustering by the surface area of the union (bvh_ploc.cu); node boxes come out of the merges
