@@ -633,9 +633,18 @@ void build_bvh(Scene &s) {
     s.upload_tables();
     s.bvh_valid = false;
     const uint32_t n_inst = (uint32_t)s.h_inst.size();
-    cudaEvent_t e0, e1;
-    PB2_CUDA(cudaEventCreate(&e0));
-    PB2_CUDA(cudaEventCreate(&e1));
+    struct Events { // destroyed on every way out, exceptions included
+        cudaEvent_t e0 = nullptr, e1 = nullptr, t0 = nullptr;
+        ~Events() {
+            if (e0) cudaEventDestroy(e0);
+            if (e1) cudaEventDestroy(e1);
+            if (t0) cudaEventDestroy(t0);
+        }
+    } ev;
+    PB2_CUDA(cudaEventCreate(&ev.e0));
+    PB2_CUDA(cudaEventCreate(&ev.e1));
+    PB2_CUDA(cudaEventCreate(&ev.t0));
+    cudaEvent_t &e0 = ev.e0, &e1 = ev.e1, &t0 = ev.t0;
     PB2_CUDA(cudaEventRecord(e0, st));
 
     // ---- which mesh of which instance ----
@@ -684,7 +693,6 @@ void build_bvh(Scene &s) {
         s.d_nodes.release(), s.d_prims.release();
         s.build_stats = stats;
         s.bvh_valid = true;
-        cudaEventDestroy(e0), cudaEventDestroy(e1);
         return;
     }
     // ---- primitive array: [bottom-level records, object space][top-level records, world space] ----
@@ -736,8 +744,6 @@ void build_bvh(Scene &s) {
         if (m->blas.valid) max_blas_depth = std::max(max_blas_depth, m->blas.depth), stats.n_nodes += m->blas.n_nodes, stats.n_triangles += m->blas.n_prims;
 
     // ---- top level ----
-    cudaEvent_t t0;
-    PB2_CUDA(cudaEventCreate(&t0));
     PB2_CUDA(cudaEventRecord(t0, st));
     const uint32_t n = (uint32_t)n_top, n_leaves = (uint32_t)leaf_inst.size();
     DevBuf<PrimRec> prims_in(n);
@@ -798,7 +804,6 @@ void build_bvh(Scene &s) {
         }
         s.blas_valid = s.n_blas > 0;
     } else if ((uint64_t)s.top_node_offset + top.n_nodes > s.d_nodes.n) { // the update outgrew its room: build everything again
-        cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(t0);
         s.blas_valid = false;
         build_bvh(s);
         return;
@@ -810,7 +815,6 @@ void build_bvh(Scene &s) {
     float ms = 0.f, top_ms = 0.f;
     PB2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     PB2_CUDA(cudaEventElapsedTime(&top_ms, t0, e1));
-    cudaEventDestroy(e0), cudaEventDestroy(e1), cudaEventDestroy(t0);
 
     s.root = s.top_node_offset;
     s.n_nodes = s.top_node_offset + top.n_nodes;

@@ -189,11 +189,7 @@ bool radix_sort_pairs(cudaStream_t st, uint64_t *keys, uint64_t *keys_alt, uint3
     PB2_LAUNCH_CHECK();
     k_sort_scan<<<n_passes, 256, 0, st>>>(hist.ptr);
     PB2_LAUNCH_CHECK();
-    static bool attr_set = false;
-    if (!attr_set) {
-        PB2_CUDA(cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
-        attr_set = true;
-    }
+    PB2_CUDA(cudaFuncSetAttribute(k_sort_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem))); // per device: set every time
     uint64_t *kin = keys, *kout = keys_alt;
     uint32_t *vin = vals, *vout = vals_alt;
     for (int p = 0; p < n_passes; ++p) {

@@ -10,6 +10,7 @@
 //   "bsdf"     in0 pb2_kat_bsdf[n], in1 float[n][8] (wo, wi, rng bits) out float[n][16] sample: wi f pdf type rng | eval: f pdf
 //   "emitter"  in0 pb2_emitter[n], in1 float[n][8] (hit_pos, hit_n, xi), in2 float[n][12] (emit_pos, emit_n, uv, scatter)
 //                                                                      out float[n][16] sample: radiance wi distance pdf | eval: radiance pdf
+//   "sort"     in0 uint64[n] keys, in2 uint32[2] (begin_bit, end_bit)      out uint32[n]  input positions in sorted order (radix_sort.cu)
 //   "select"   in0 pb2_emitter[m] (m = in2[0] as uint32, has_env = in2[1]), in1 float[n] p   out int32[n] index (m = env, -1 none)
 #include "../scene.cuh"
 #include "../pt_math.cuh"
@@ -28,6 +29,7 @@ struct KatBsdf { // mirrors LocalBsdf; slots c0..c2 as in pb2_material
 DevTexture to_dev(const pb2_texture &t);
 DevEmitter to_dev(const pb2_emitter &e);
 std::vector<float> area_select_cdf(const DevEmitter *areas, size_t n);
+bool radix_sort_pairs(cudaStream_t st, uint64_t *keys, uint64_t *keys_alt, uint32_t *vals, uint32_t *vals_alt, uint32_t n, int begin_bit, int end_bit);
 
 namespace {
 __global__ void k_rng(const uint32_t *in, uint64_t n, float *out) {
@@ -214,6 +216,19 @@ int run_kat(const char *what_c, const void *in0, const void *in1, const void *in
         PB2_LAUNCH_CHECK();
         PB2_CUDA(cudaDeviceSynchronize());
         PB2_CUDA(cudaMemcpy(out, o.ptr, o.bytes(), cudaMemcpyDeviceToHost));
+        return PB2_OK;
+    }
+    if (what == "sort") { // radix_sort.cu: in0 = uint64 keys[n], in2 = uint32 {begin_bit, end_bit}; out = uint32[n]: the input positions in sorted order
+        const uint32_t begin_bit = static_cast<const uint32_t *>(in2)[0], end_bit = static_cast<const uint32_t *>(in2)[1];
+        auto keys = up<uint64_t>(in0, n);
+        std::vector<uint32_t> iota(n);
+        for (uint64_t i = 0; i < n; ++i) iota[i] = (uint32_t)i;
+        auto vals = up<uint32_t>(iota.data(), n);
+        DevBuf<uint64_t> keys_alt(n);
+        DevBuf<uint32_t> vals_alt(n);
+        const bool alt = radix_sort_pairs(nullptr, keys.ptr, keys_alt.ptr, vals.ptr, vals_alt.ptr, (uint32_t)n, (int)begin_bit, (int)end_bit);
+        PB2_CUDA(cudaDeviceSynchronize());
+        PB2_CUDA(cudaMemcpy(out, alt ? vals_alt.ptr : vals.ptr, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         return PB2_OK;
     }
     throw std::runtime_error("pb2_kat: unknown function '" + what + "'");

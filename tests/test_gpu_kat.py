@@ -300,3 +300,18 @@ def test_select_emitter_large_table_matches_the_linear_scan(port_lib):
         out = np.zeros(len(ps), np.int32)
         pb2.kat("select", parr, ps, np.array([m, has_env], np.uint32), len(ps), out)
         assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 4095, 4096, 4097, 100_003, 3_000_001])
+def test_radix_sort_is_a_stable_sort(n):
+    """csrc/radix_sort.cu (the BVH builders' Morton sort): the permutation of a stable sort by the chosen key bits, for ragged
+    tile counts, heavy duplicates and partial bit ranges"""
+    rng = np.random.default_rng(n)
+    cases = [(rng.integers(0, 1 << 63, n, dtype=np.uint64), 0, 63),                      # full 63-bit Morton keys
+             (rng.integers(0, 7, n, dtype=np.uint64) << np.uint64(20), 0, 63),            # seven distinct keys: stability decides the order
+             (rng.integers(0, 1 << 40, n, dtype=np.uint64), 8, 32)]                       # three passes over a bit window: an odd pass count
+    for keys, b0, b1 in cases:
+        out = np.zeros(n, np.uint32)
+        pb2.kat("sort", keys, None, np.array([b0, b1], np.uint32), n, out)
+        window = (keys >> np.uint64(b0)) & np.uint64((1 << (b1 - b0)) - 1)
+        assert np.array_equal(out, np.argsort(window, kind="stable").astype(np.uint32))
