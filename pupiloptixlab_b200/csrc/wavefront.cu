@@ -143,7 +143,8 @@ __device__ __forceinline__ uint32_t warp_append_keyed(uint32_t *counters, uint32
 }
 
 // ---- generate: main.cu:50-78 ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_generate(PathArrays pa, FrameParams fp, Camera cam, uint32_t *__restrict__ q_ext, uint32_t n_paths) {
+__global__ void __launch_bounds__(256) k_generate(PathArrays pa, FrameParams fp, Camera cam, uint32_t *__restrict__ q_ext, uint32_t n_paths, uint32_t *__restrict__ n_ext) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_ext = n_paths; // size of the first extension queue (was a pageable H2D copy from a stack variable per batch)
     for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += gridDim.x * blockDim.x) {
         const uint32_t frame = p / fp.n_pixels, pixel = p - frame * fp.n_pixels;
         const uint32_t y = pixel / fp.width, x = pixel - y * fp.width;
@@ -724,10 +725,9 @@ void render(Scene &s, const pb2_launch_params &lp) {
         if (batch == 1 && n_lanes == 2) PB2_CUDA(cudaStreamWaitEvent(st, wf.stagger, 0));
         PB2_CUDA(cudaMemsetAsync(ln.counters.ptr, 0, ln.counters.bytes(), st));
         stage_begin(0);
-        k_generate<<<grid_stream, 256, 0, st>>>(pa, fp, s.cam, ln.q_ext[0].ptr, n_paths);
+        k_generate<<<grid_stream, 256, 0, st>>>(pa, fp, s.cam, ln.q_ext[0].ptr, n_paths, ln.counters.ptr + CTR_EXT);
         PB2_LAUNCH_CHECK();
         stage_end();
-        PB2_CUDA(cudaMemcpyAsync(ln.counters.ptr + CTR_EXT, &n_paths, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         ++wf.launches;
 
         const bool last_batch = f0 + frames >= n_frames;

@@ -58,6 +58,30 @@ def test_c1_cornell_512_one_sample(port_lib):
     assert abs(int(rs.closest_rays) - int(ref["closest_rays"])) <= 0.002 * ref["closest_rays"]
 
 
+@pytest.mark.parametrize("name,maker,min_match", [("c2_cornell", lambda: scenes.cornell_box(1920, 1080, 8), 0.999),
+                                                  ("c3_material_grid", lambda: scenes.material_grid(1920, 1080, 8), 0.97)])
+def test_c2_c3_full_hd_frame_against_the_oracle_on_a_pixel_sample(port_lib, name, maker, min_match):
+    """BASELINE.json configs[1] / configs[2] at their frame size: one 1920 x 1080 frame through the whole path, 6000 pixels of it
+    against the oracle's per-pixel loop (same seed); the RNG-only `test` buffer of the whole frame is bit-exact"""
+    desc = maker()
+    pupil.load_scene(desc)
+    pupil.pass_config()
+    pupil.run(1)
+    frame, test = pupil.buffer("final result"), pupil.buffer("test")
+    assert frame.shape == (1080, 1920, 4) and np.isfinite(frame).all()
+    osc = orc.OracleScene(port_lib, desc)
+    rng = np.random.default_rng(8)
+    xs, ys = rng.integers(0, 1920, 6000), rng.integers(0, 1080, 6000)
+    ref = np.stack([osc.render_pixel(int(x), int(y), seed=0)[0] for x, y in zip(xs, ys)])
+    got = frame[ys, xs, :3]
+    ok = (np.abs(got - ref) <= 1e-4 * np.maximum(1.0, np.abs(ref))).all(1)
+    assert ok.mean() >= min_match, f"{name}: {ok.mean() * 100:.2f}% of the sampled pixels within 1e-4"
+    assert abs(got.mean() - ref.mean()) <= 0.02 * ref.mean()
+    strip = orc.OracleScene(port_lib, maker()).render(1)["test"].reshape(1080, 1920) if name == "c2_cornell" else None
+    if strip is not None:
+        assert np.array_equal(test.reshape(1080, 1920), strip)
+
+
 @pytest.fixture(scope="module")
 def terrain_30m(port_lib):
     desc = scenes.terrain(3873, 1920, 1080, 8)
