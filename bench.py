@@ -599,7 +599,7 @@ def main():
                        "sharding": (f"sample-index (seed = base + rank + k*{world}) inside the product: PTPass::SetShard -> pb2_shard_plan, plain sums, "
                                     f"pb2_comm_reduce_frames ({'ncclReduceScatter + finalize + ncclAllGather' if args.reduce == 'all' else 'ncclReduce to rank 0 + finalize'}) "
                                     "on its own stream, overlapped with the next step's render") if world > 1 else "none",
-                       "l2": "path-state working set per batch (32 Mi paths, ~4.7 GB) and accumulation buffers exceed the 126 MB L2; no explicit flush"},
+                       "l2": "path-state working set per batch (up to 128 Mi paths, ~18.8 GB; here one batch of 64 frames) and accumulation buffers exceed the 126 MB L2; no explicit flush"},
             "mrays_per_s": mrays, "rays_per_sample": (closest_all + shadow_all) / (n_px * spp_step_total * args.steps),
             "bvh": {"build_ms": build.build_ms, "n_prims": build.n_prims, "n_nodes": build.n_nodes, "bytes": build.bvh_bytes, "sah_cost": build.sah_cost},
             "scene_load_s": load_s, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,

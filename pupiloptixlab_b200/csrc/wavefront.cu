@@ -662,8 +662,9 @@ void render(Scene &s, const pb2_launch_params &lp) {
     const uint32_t n_frames = std::max(1u, lp.n_frames);
     // paths in flight: measured on the Cornell box at 1080p (profiles/README.md) 2 Mi -> 927, 4 Mi -> 1054, 16 Mi -> 1202,
     // 32 Mi -> 1226, 64 Mi -> 1239 Msamples/s with one batch in flight (later bounces leave short queues; bigger batches
-    // amortise their launch gaps and tails).  32 Mi paths = 4.7 GB of path state out of 180 GB, shared by the two lanes.
-    const uint64_t target = s.paths_in_flight ? s.paths_in_flight : (32ull << 20);
+    // amortise their launch gaps and tails).  Round 2, final kernels: 32 Mi -> 1508, 64 Mi -> 1523, 128 Mi -> 1537 Msamples/s.  The default
+    // is 128 Mi paths = 18.8 GB of path state out of 180 GB (allocated only as far as a render call needs it), shared by the two lanes.
+    const uint64_t target = s.paths_in_flight ? s.paths_in_flight : (128ull << 20);
     const uint32_t n_lanes = (s.two_lanes && n_frames >= 2) ? 2u : 1u;
     const uint32_t S = (uint32_t)std::min<uint64_t>((n_frames + n_lanes - 1) / n_lanes, std::max<uint64_t>(1, target / n_lanes / n_pixels));
     const uint32_t rounds = std::max(1u, lp.max_depth);
