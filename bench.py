@@ -466,6 +466,12 @@ def main():
         n_ext, n_shade, n_shadow = n_ext + rs.extend_launches, n_shade + rs.shade_launches, n_shadow + rs.shadow_launches
     pupil.synchronize()  # the last step's reduction; then the end event on the launching stream
     e1.record(stream)
+    reduce_rec = None
+    if world > 1:  # the last reduction of the timed region: nothing ran beside it, so this is the collective + finalize alone
+        r_ms, r_bytes = pupil.last_reduction()
+        reduce_rec = {"ms": r_ms, "bytes_per_rank": r_bytes, "gbs_per_rank": r_bytes / (r_ms * 1e-3) / 1e9 if r_ms > 0 else None,
+                      "collective": "ncclReduce to rank 0 + finalize" if args.reduce == "root" else "ncclReduceScatter + finalize + ncclAllGather",
+                      "note": "overlapped with the next step's render in steady state; exposed only after the last step"}
     barrier()
     clocks = sampler.stop() if rank == 0 else {}
     ms = e0.elapsed_time(e1)
@@ -604,6 +610,8 @@ def main():
             "bvh": {"build_ms": build.build_ms, "n_prims": build.n_prims, "n_nodes": build.n_nodes, "bytes": build.bvh_bytes, "sah_cost": build.sah_cost},
             "scene_load_s": load_s, "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
         }
+        if reduce_rec:
+            line["reduce"] = reduce_rec
         line.update(sub)
         print(json.dumps(line), flush=True)
     if world > 1:

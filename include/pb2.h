@@ -252,6 +252,8 @@ int pb2_comm_destroy(pb2_comm *comm);
 int pb2_comm_reduce_frames(pb2_comm *comm, pb2_scene *scene, const void *sum_buffer, void *frame_buffer, uint64_t n_pixels, uint32_t total_spp,
                            int mode, int root);
 int pb2_comm_synchronize(pb2_comm *comm);
+/* device time of the last pb2_comm_reduce_frames (collectives + finalize) and the bytes of one rank's sum buffer; synchronises */
+int pb2_comm_last_reduction(pb2_comm *comm, float *ms, uint64_t *bytes);
 int pb2_comm_nccl_version(int *version);
 /* the seeds of `rank` in progressive step `step`: first_seed + k * seed_stride, k < spp_rank.  strong = 0: every rank renders
  * `spp` frames (the step holds spp * n_ranks); strong = 1: the step's `spp` frames are split over the ranks. */

@@ -58,6 +58,7 @@ int pupil_comm_unique_id(uint8_t id[128]);
 int pupil_set_shard(int rank, int world, const uint8_t *id, int strong, int reduce_mode);
 int pupil_set_shard_plan(int strong); /* switch between the weak and the strong plan, keeping the communicator */
 int pupil_synchronize(void);
+int pupil_last_reduction(float *ms, uint64_t *bytes); /* pb2_comm_last_reduction of the pass's communicator */
 /* System::Run() for n_pass_runs iterations of the pass list (headless: returns instead of looping forever) */
 int pupil_run(uint64_t n_pass_runs);
 /* frames (samples per pixel) accumulated so far and the next random_seed */

@@ -66,6 +66,8 @@ struct Comm {
     int rank = 0, size = 1, device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t scene_ready = nullptr, done = nullptr;
+    cudaEvent_t t_begin = nullptr, t_end = nullptr; // device time of the last reduction (on the communicator's stream)
+    uint64_t last_bytes = 0;
     DevBuf<float4> staging; // reduced sums: the whole image on the root (ROOT mode) or this rank's slice (ALL mode)
     uint64_t reductions = 0;
     ~Comm() {
@@ -73,6 +75,8 @@ struct Comm {
         if (comm) nccl().CommDestroy(comm);
         if (scene_ready) cudaEventDestroy(scene_ready);
         if (done) cudaEventDestroy(done);
+        if (t_begin) cudaEventDestroy(t_begin);
+        if (t_end) cudaEventDestroy(t_end);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -96,6 +100,8 @@ Comm *comm_create(int n_ranks, int rank, const uint8_t *id) {
     PB2_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi));
     PB2_CUDA(cudaEventCreateWithFlags(&c->scene_ready, cudaEventDisableTiming));
     PB2_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+    PB2_CUDA(cudaEventCreate(&c->t_begin));
+    PB2_CUDA(cudaEventCreate(&c->t_end));
     if (n_ranks > 1) { // a single rank needs no NCCL at all
         if (!id) throw std::runtime_error("pb2_comm_create: the id of pb2_comm_unique_id (from rank 0) is required for more than one rank");
         ncclUniqueId u;
@@ -113,6 +119,8 @@ void comm_reduce_frames(Comm &c, Scene &s, const float4 *sum, float4 *frame, uin
     if (root < 0 || root >= c.size) throw std::runtime_error("pb2_comm_reduce_frames: bad root");
     PB2_CUDA(cudaEventRecord(c.scene_ready, s.stream));
     PB2_CUDA(cudaStreamWaitEvent(c.stream, c.scene_ready, 0));
+    PB2_CUDA(cudaEventRecord(c.t_begin, c.stream));
+    c.last_bytes = n_pixels * sizeof(float4);
     if (c.size == 1) {
         if (!frame) throw std::runtime_error("pb2_comm_reduce_frames: frame buffer missing");
         finalize_sum_on(c.stream, sum, frame, n_pixels, total_spp);
@@ -131,6 +139,7 @@ void comm_reduce_frames(Comm &c, Scene &s, const float4 *sum, float4 *frame, uin
         nccl_check(nccl().Reduce(sum, c.rank == root ? c.staging.ptr : nullptr, n_pixels * 4, ncclFloat, ncclSum, root, c.comm, c.stream), "ncclReduce");
         if (c.rank == root) finalize_sum_on(c.stream, c.staging.ptr, frame, n_pixels, total_spp);
     }
+    PB2_CUDA(cudaEventRecord(c.t_end, c.stream));
     PB2_CUDA(cudaEventRecord(c.done, c.stream));
     // the sum buffer is being read: the scene's next k_accumulate waits for this reduction (wavefront.cu).  The event belongs
     // to the scene, so neither object's lifetime depends on the other's.
@@ -140,6 +149,15 @@ void comm_reduce_frames(Comm &c, Scene &s, const float4 *sum, float4 *frame, uin
     ++c.reductions;
 }
 void comm_synchronize(Comm &c) { PB2_CUDA(cudaStreamSynchronize(c.stream)); }
+// device time of the last reduction (collectives + finalize, from the moment the communicator's stream could start on it) and the
+// bytes of one rank's sum buffer; synchronises the communicator's stream
+void comm_last_reduction(Comm &c, float *ms, uint64_t *bytes) {
+    PB2_CUDA(cudaStreamSynchronize(c.stream));
+    float t = 0.f;
+    if (c.reductions) PB2_CUDA(cudaEventElapsedTime(&t, c.t_begin, c.t_end));
+    if (ms) *ms = t;
+    if (bytes) *bytes = c.last_bytes;
+}
 int comm_nccl_version() {
     int v = 0;
     nccl_check(nccl().GetVersion(&v), "ncclGetVersion");

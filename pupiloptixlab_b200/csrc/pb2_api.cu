@@ -658,6 +658,13 @@ int pb2_comm_synchronize(pb2_comm *comm) {
     return PB2_OK;
     PB2_CATCH
 }
+int pb2_comm_last_reduction(pb2_comm *comm, float *ms, uint64_t *bytes) {
+    PB2_TRY
+    if (!comm) return fail(PB2_ERR_ARG, "pb2_comm_last_reduction: null");
+    comm_last_reduction(*reinterpret_cast<Comm *>(comm), ms, bytes);
+    return PB2_OK;
+    PB2_CATCH
+}
 int pb2_comm_nccl_version(int *version) {
     PB2_TRY
     if (!version) return fail(PB2_ERR_ARG, "pb2_comm_nccl_version: null");

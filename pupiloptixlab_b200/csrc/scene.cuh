@@ -112,6 +112,7 @@ Comm *comm_create(int n_ranks, int rank, const uint8_t *id);
 void comm_destroy(Comm *c);
 void comm_reduce_frames(Comm &c, Scene &s, const float4 *sum, float4 *frame, uint64_t n_pixels, uint32_t total_spp, int mode, int root);
 void comm_synchronize(Comm &c);
+void comm_last_reduction(Comm &c, float *ms, uint64_t *bytes);
 int comm_nccl_version();
 // test_hooks/kat.cu (libpb2_kat.so, not part of libpb2.so)
 int run_kat(const char *what, const void *in0, const void *in1, const void *in2, uint64_t n, void *out);

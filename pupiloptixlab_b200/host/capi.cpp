@@ -184,6 +184,10 @@ int pupil_set_shard_plan(int strong) {
     g_pass->SetShard(g_comm, g_rank, g_world, strong != 0, g_reduce_mode); // same communicator, other split of the step's seeds
     return 0;
 }
+int pupil_last_reduction(float *ms, uint64_t *bytes) {
+    if (!Ready() || !g_comm) return Fail("pupil_set_shard first");
+    return pb2_comm_last_reduction(g_comm, ms, bytes) == PB2_OK ? 0 : Fail(pb2_last_error());
+}
 int pupil_synchronize(void) {
     if (!Ready()) return Fail("pupil_init first");
     g_pass->Synchronize();

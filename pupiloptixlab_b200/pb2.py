@@ -101,7 +101,7 @@ def lib():
             "pb2_render_stats_get": [vp, P(RenderStats)], "pb2_scene_set_option": [vp, C.c_char_p, C.c_int64],
             "pb2_finalize_sum": [vp, vp, vp, u64, u32],
             "pb2_comm_unique_id": [vp], "pb2_comm_create": [P(vp), C.c_int, C.c_int, vp], "pb2_comm_destroy": [vp],
-            "pb2_comm_reduce_frames": [vp, vp, vp, vp, u64, u32, C.c_int, C.c_int], "pb2_comm_synchronize": [vp], "pb2_comm_nccl_version": [P(C.c_int)],
+            "pb2_comm_reduce_frames": [vp, vp, vp, vp, u64, u32, C.c_int, C.c_int], "pb2_comm_synchronize": [vp], "pb2_comm_nccl_version": [P(C.c_int)], "pb2_comm_last_reduction": [vp, P(f32), P(u64)],
             "pb2_shard_plan": [C.c_int, C.c_int, u32, u32, C.c_int, P(u32), P(u32), P(u32), P(u32)],
         }
         for name, args in sigs.items():

@@ -57,7 +57,7 @@ def lib():
             "pupil_image_save": [C.c_char_p, vp, u32, u32, C.c_int], "pupil_save_buffer": [C.c_char_p, C.c_char_p, C.c_int],
             "pupil_get_env_tables": [P(u32), P(u32), vp, vp, vp], "pupil_set_instance_transform": [u32, P(f32)],
             "pupil_remove_instance": [u32], "pupil_comm_unique_id": [vp], "pupil_set_shard": [C.c_int, C.c_int, vp, C.c_int, C.c_int],
-            "pupil_synchronize": [], "pupil_set_shard_plan": [C.c_int],
+            "pupil_synchronize": [], "pupil_set_shard_plan": [C.c_int], "pupil_last_reduction": [P(f32), P(u64)],
             "pupil_register_mesh_borrowed": [C.c_char_p, vp, vp, vp, vp, u32, u32], "pupil_unregister_mesh": [C.c_char_p],
             "pupil_checkpoint_save": [C.c_char_p], "pupil_checkpoint_load": [C.c_char_p],
         }
@@ -204,6 +204,13 @@ def set_shard(rank: int, world: int, comm_id: bytes | None, strong: bool = False
 
 def set_shard_plan(strong: bool):
     check(lib().pupil_set_shard_plan(int(strong)))
+
+
+def last_reduction():
+    """(device ms, bytes of one rank's sum buffer) of the last multi-GPU reduction; waits for it"""
+    ms, nbytes = f32(), u64()
+    check(lib().pupil_last_reduction(C.byref(ms), C.byref(nbytes)))
+    return ms.value, nbytes.value
 
 
 def synchronize():
