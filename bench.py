@@ -431,6 +431,8 @@ def main():
     for kv in args.opt:
         k, v = kv.split("=")
         scene.set_option(k, int(v))
+    if any(kv.startswith(("collapse", "ploc_radius")) for kv in args.opt):
+        scene.build()  # options that change the tree invalidate it
     build = pupil.build_stats()
 
     def step(i: int):

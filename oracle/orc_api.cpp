@@ -159,6 +159,26 @@ void orc_trace_closest(void *sp, const float *rays, uint64_t n, orc_hit *hits, i
     for (auto &t : pool) t.join();
     if (n_prim_tests) *n_prim_tests = tests;
 }
+/* exhaustive loop with the instances flagged in objspace[instance] intersected in OBJECT space (orc_render.h: trace_brute_objspace) */
+void orc_trace_closest_objspace(void *sp, const float *rays, uint64_t n, orc_hit *hits, const uint8_t *objspace, int threads) {
+    auto *s = static_cast<SceneT *>(sp);
+    if (threads <= 0) threads = (int)std::max(1u, std::thread::hardware_concurrency());
+    std::atomic<uint64_t> next{ 0 };
+    auto worker = [&]() {
+        for (;;) {
+            uint64_t b = next.fetch_add(64);
+            if (b >= n) break;
+            for (uint64_t i = b; i < std::min(n, b + 64); ++i) {
+                const float *r = rays + i * 8;
+                hits[i] = s->trace_brute_objspace(v3(r), v3(r + 4), r[3], r[7], objspace);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+}
 void orc_trace_any(void *sp, const float *rays, uint64_t n, uint8_t *occluded, int brute) {
     auto *s = static_cast<SceneT *>(sp);
     for (uint64_t i = 0; i < n; ++i) {

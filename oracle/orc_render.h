@@ -264,6 +264,50 @@ struct Scene {
             if (hit_sphere(s, o, d, tmin, tmax, t) && better(t, s.inst, 0, h)) h = orc_hit{ t, 0.f, 0.f, s.inst, 0 };
         }
     }
+    // ---------- meshes behind an instance (IAS -> GAS, framework/world/ias_manager.cpp:29-114, gas_manager.cpp:10) ----------
+    // OptiX moves the ray into the instance's object space with the inverse of its 3x4 transform and intersects the shared,
+    // untransformed triangles there; t keeps its meaning because the direction is not renormalised.  This restates exactly
+    // that for the instances flagged in `objspace`, with the arithmetic the device library spells out: the inverse is the
+    // fp64 adjugate rounded once to fp32 (pupiloptixlab_b200/csrc/pb2_api.cu, invert_affine), point and vector transforms and
+    // the triangle test are the ix_* sequences above.  Everything else is tested in world space as in trace_brute.
+    static void invert_affine_f64(const float *m, float *out) {
+        const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+        const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+        const double id = 1.0 / det;
+        const double r[9] = { (e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id, (f * g - d * i) * id, (a * i - c * g) * id,
+                              (c * d - a * f) * id, (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id };
+        const double tx = m[3], ty = m[7], tz = m[11];
+        for (int k = 0; k < 3; ++k) {
+            out[k * 4 + 0] = (float)r[k * 3], out[k * 4 + 1] = (float)r[k * 3 + 1], out[k * 4 + 2] = (float)r[k * 3 + 2];
+            out[k * 4 + 3] = (float)-(r[k * 3] * tx + r[k * 3 + 1] * ty + r[k * 3 + 2] * tz);
+        }
+    }
+    orc_hit trace_brute_objspace(f3 o, f3 d, float tmin, float tmax, const uint8_t *objspace) const {
+        orc_hit h{ 0.f, 0.f, 0.f, -1, -1 };
+        for (int i = 0; i < (int)tris.size(); ++i)
+            if (!objspace[tris[i].inst]) test_prim(i, o, d, tmin, tmax, h, nullptr);
+        for (int i = 0; i < (int)spheres.size(); ++i) test_prim(-1 - i, o, d, tmin, tmax, h, nullptr);
+        for (size_t ii = 0; ii < instances.size(); ++ii) {
+            const Instance &in = instances[ii];
+            if (!objspace[ii] || in.shape_type == ORC_SHAPE_SPHERE) continue;
+            float inv[12];
+            invert_affine_f64(in.xf.e, inv);
+            const f3 oo = ix_point(o, inv), dd = ix_vector(d, inv);
+            const MeshData &md = meshes[in.mesh];
+            const size_t nf = md.idx.size() / 3;
+            for (size_t f = 0; f < nf; ++f) {
+                f3 p[3];
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t vi = md.idx[f * 3 + k];
+                    p[k] = f3{ md.pos[vi * 3], md.pos[vi * 3 + 1], md.pos[vi * 3 + 2] };
+                }
+                const WorldTri ot{ p[0], p[1] - p[0], p[2] - p[0], (int)ii, (int)f };
+                float t, u, v;
+                if (hit_tri(ot, oo, dd, tmin, tmax, t, u, v) && better(t, ot.inst, ot.prim, h)) h = orc_hit{ t, u, v, ot.inst, ot.prim };
+            }
+        }
+        return h;
+    }
     orc_hit trace_brute(f3 o, f3 d, float tmin, float tmax) const {
         orc_hit h{ 0.f, 0.f, 0.f, -1, -1 };
         for (int i = 0; i < (int)tris.size(); ++i) test_prim(i, o, d, tmin, tmax, h, nullptr);

@@ -215,8 +215,33 @@ __global__ void k_radix_tree(const uint64_t *__restrict__ keys, BinTree t) {
 // weight_src != nullptr (top-level build with instance leaves): range.y becomes a WEIGHTED primitive count in which an instance
 // leaf counts kLeafMax + 1, so no subtree that holds one is ever folded into a leaf slot and the collapse reaches it on its own.
 __device__ __forceinline__ int leaf_weight(const PrimRec *prims, uint32_t p) { return __float_as_uint(prims[p].e2.w) == 2u ? kLeafMax + 1 : 1; }
+// COST: the same bottom-up sweep also fills the tables of the cost-optimal collapse (Ylitie, Karras, Laine 2017, "Efficient
+// incoherent ray traversal on GPUs through compressed wide BVHs", section 4.1).  For a binary node n and a budget of i slots,
+//   C(n, 1) = A(n) count(n) c_prim                       when the subtree fits a leaf slot (count <= kLeafMax)
+//           = A(n) c_node + min_k C(l, k) + C(r, 8 - k)   otherwise: n becomes a wide node of its own
+//   C(n, i) = min(C(n, i - 1), min_k C(l, k) + C(r, i - k)),   i = 2 .. 7
+// with A the half surface area and C(leaf, i) = A c_prim.  A node keeps C(n, 1..7) (32 bytes) for its parent and one word of
+// decisions for the top-down pass of k_collapse: three bits per budget i = 2 .. 8 holding the k of the best split, 0 = "the
+// answer for i - 1 is at least as good".  The greedy largest-area expansion this replaces (collapse = 0) spends a wide node on
+// every subtree of 4 .. 8 primitives it meets; on the 30 M-triangle terrain that gave 6.8 primitives per 80-byte node.
+struct CostTab {
+    float4 *c;      // [2 * node], [2 * node + 1]: C(node, 1..4), C(node, 5..7)
+    uint32_t *word; // decisions
+    float c_prim;   // cost of one primitive test in units of one wide-node test
+};
+__device__ __forceinline__ void load_cost(const CostTab &ct, int ref, float3 lo, float3 hi, int weight, float C[7]) {
+    if (ref >= 0) {
+        const float4 a = __ldcg(&ct.c[2 * (size_t)ref]), b = __ldcg(&ct.c[2 * (size_t)ref + 1]);
+        C[0] = a.x, C[1] = a.y, C[2] = a.z, C[3] = a.w, C[4] = b.x, C[5] = b.y, C[6] = b.z;
+    } else {
+        const float v = half_area(lo, hi) * (weight > kLeafMax ? 1.f : ct.c_prim); // an instance leaf costs a node step whatever the budget
+#pragma unroll
+        for (int i = 0; i < 7; ++i) C[i] = v;
+    }
+}
+template<bool COST>
 __global__ void k_refit(BinTree t, const uint32_t *__restrict__ sorted, const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi,
-                        int *__restrict__ arrive, const PrimRec *__restrict__ weight_src) {
+                        int *__restrict__ arrive, const PrimRec *__restrict__ weight_src, CostTab ct) {
     const int n = t.n, j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     int node = t.parent[(n - 1) + j];
@@ -232,10 +257,39 @@ __global__ void k_refit(BinTree t, const uint32_t *__restrict__ sorted, const fl
         const float3 lo = fmin3(llo, rlo), hi = fmax3(lhi, rhi);
         t.lo[node] = make_float4(lo.x, lo.y, lo.z, 0.f);
         t.hi[node] = make_float4(hi.x, hi.y, hi.z, 0.f);
-        if (weight_src) {
-            const int wl = lc >= 0 ? __ldcg(&t.range[lc]).y : leaf_weight(weight_src, sorted[~lc]);
-            const int wr = rc >= 0 ? __ldcg(&t.range[rc]).y : leaf_weight(weight_src, sorted[~rc]);
-            t.range[node].y = wl + wr;
+        if (weight_src || COST) {
+            const int wl = lc >= 0 ? __ldcg(&t.range[lc]).y : weight_src ? leaf_weight(weight_src, sorted[~lc]) : 1;
+            const int wr = rc >= 0 ? __ldcg(&t.range[rc]).y : weight_src ? leaf_weight(weight_src, sorted[~rc]) : 1;
+            if (weight_src) t.range[node].y = wl + wr;
+            if (COST) {
+                float Cl[7], Cr[7], C[7];
+                load_cost(ct, lc, llo, lhi, wl, Cl);
+                load_cost(ct, rc, rlo, rhi, wr, Cr);
+                float dist[9];
+                uint32_t kb[9];
+#pragma unroll
+                for (int i = 2; i <= 8; ++i) {
+                    dist[i] = FLT_MAX, kb[i] = 1u;
+#pragma unroll
+                    for (int k = 1; k <= 7; ++k) {
+                        if (k >= i || i - k > 7) continue;
+                        const float v = Cl[k - 1] + Cr[i - k - 1];
+                        if (v < dist[i]) dist[i] = v, kb[i] = (uint32_t)k;
+                    }
+                }
+                const float A = half_area(lo, hi);
+                const int cnt = wl + wr;
+                C[0] = cnt <= kLeafMax ? A * (float)cnt * ct.c_prim : A + dist[8];
+                uint32_t word = kb[8] << 18;
+#pragma unroll
+                for (int i = 2; i <= 7; ++i) {
+                    if (dist[i] < C[i - 2]) C[i - 1] = dist[i], word |= kb[i] << (3 * (i - 2));
+                    else C[i - 1] = C[i - 2];
+                }
+                ct.c[2 * (size_t)node] = make_float4(C[0], C[1], C[2], C[3]);
+                ct.c[2 * (size_t)node + 1] = make_float4(C[4], C[5], C[6], 0.f);
+                ct.word[node] = word;
+            }
         }
         __threadfence();
         node = t.parent[node];
@@ -253,6 +307,7 @@ struct CollapseCtx {
     uint32_t *counters; // [0] nodes allocated, [1] prims allocated, [2] next-level queue size, [3] max depth
     float *sah;         // [0] accumulated SAH cost (un-normalised)
     bool inst_leaves;   // top-level build: primitive records of kind 2 become instance nodes
+    const uint32_t *word; // decisions of the cost-optimal collapse (k_refit<true>), nullptr: greedy largest-area expansion
 };
 struct Ref {
     float3 lo, hi;
@@ -311,6 +366,25 @@ __global__ void __launch_bounds__(128, PB2_COLLAPSE_MINB) k_collapse(CollapseCtx
     int n = 0;
     const bool is_instance = c.inst_leaves && self.ref < 0 && self.count > kLeafMax; // writes an instance node, has no children
     if (is_instance) {
+    } else if (c.word && self.ref >= 0 && self.count > kLeafMax) {
+        // the cut below this node that the tables of k_refit<true> found cheapest: hand the eight slots down the binary tree
+        int st_ref[8], st_i[8], sp = 0;
+        st_ref[sp] = self.ref, st_i[sp++] = 8;
+        while (sp > 0) {
+            const int m = st_ref[--sp];
+            int i = st_i[sp];
+            uint32_t k = 0;
+            if (m >= 0 && i > 1) {
+                const uint32_t w = c.word[m];
+                while (i > 1 && (k = (w >> (3 * (i - 2))) & 7u) == 0u) --i;
+            }
+            if (m < 0 || i == 1) {
+                ch[n++] = load_ref(c, m);
+                continue;
+            }
+            st_ref[sp] = c.t.right[m], st_i[sp++] = i - (int)k;
+            st_ref[sp] = c.t.left[m], st_i[sp++] = (int)k;
+        }
     } else if (self.ref >= 0 && self.count > 1) {
         ch[n++] = load_ref(c, c.t.left[self.ref]);
         ch[n++] = load_ref(c, c.t.right[self.ref]);
@@ -535,6 +609,8 @@ void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, 
     DevBuf<float4> nlo(n), nhi(n);
     BinTree t{ left.ptr, right.ptr, parent.ptr, range.ptr, nlo.ptr, nhi.ptr, n };
     int root_ref = 0; // binary node the collapse starts from (node 0 for the top-down builders)
+    DevBuf<float4> cost_c;      // cost-optimal collapse (Scene::collapse = 1, LBVH): filled by k_refit<true>, read by k_collapse
+    DevBuf<uint32_t> cost_word;
     {
         // 63-bit Morton keys, sorted by the in-tree onesweep radix sort (radix_sort.cu: eight 8-bit passes; measured against
         // cub::DeviceRadixSort on the 30 M-triangle terrain: 380 vs 347 us per pass, the whole build 12.9 vs 12.8 ms)
@@ -558,7 +634,13 @@ void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, 
             PB2_LAUNCH_CHECK();
             DevBuf<int> arrive(n);
             arrive.zero(st);
-            k_refit<<<div_up(n, 256), 256, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr, inst_leaves ? prims_in.ptr : nullptr);
+            if (s.collapse == 1) {
+                cost_c.alloc(2 * (size_t)n), cost_word.alloc(n);
+                const CostTab ct{ cost_c.ptr, cost_word.ptr, (float)s.collapse_prim_cost_pct * 0.01f };
+                k_refit<true><<<div_up(n, 256), 256, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr, inst_leaves ? prims_in.ptr : nullptr, ct);
+            } else {
+                k_refit<false><<<div_up(n, 256), 256, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr, inst_leaves ? prims_in.ptr : nullptr, CostTab{});
+            }
             PB2_LAUNCH_CHECK();
         }
         PB2_CUDA(cudaStreamSynchronize(st)); // tmp / arrive / keys go out of scope
@@ -575,7 +657,7 @@ void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, 
     PB2_CUDA(cudaMemcpyAsync(qa.ptr, &root, sizeof root, cudaMemcpyHostToDevice, st));
     DevBuf<uint32_t> dst_of_sorted(n);
     PB2_CUDA(cudaMemsetAsync(dst_of_sorted.ptr, 0xff, (size_t)n * sizeof(uint32_t), st)); // records that get no leaf slot (instance leaves) stay ~0
-    CollapseCtx cc{ t, sorted.ptr, box_lo.ptr, box_hi.ptr, prims_in.ptr, dst_of_sorted.ptr, out.nodes.ptr, counters.ptr, sah.ptr, inst_leaves };
+    CollapseCtx cc{ t, sorted.ptr, box_lo.ptr, box_hi.ptr, prims_in.ptr, dst_of_sorted.ptr, out.nodes.ptr, counters.ptr, sah.ptr, inst_leaves, cost_word.ptr };
     uint32_t n_in = 1;
     uint4 *q_in = qa.ptr, *q_out = qb.ptr;
     uint32_t host_counters[4] = { 0, 0, 0, 0 };

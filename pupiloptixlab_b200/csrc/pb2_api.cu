@@ -146,6 +146,7 @@ SceneView Scene::view() const {
     v.nodes = d_nodes.ptr, v.prims = d_prims.ptr, v.instances = d_inst.ptr, v.materials = d_mat.ptr;
     v.areas = d_areas.ptr, v.env = has_env ? d_env.ptr : nullptr, v.area_cdf = d_area_cdf.ptr;
     v.n_areas = (uint32_t)h_areas.size(), v.n_nodes = n_nodes, v.n_prims = n_prims, v.root = root;
+    v.plane_bias = 0x47000000u;
     return v;
 }
 }// namespace pb2
@@ -617,6 +618,8 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);
     else if (n == "instancing") s.instancing = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)), s.bvh_valid = false, s.blas_valid = false;
     else if (n == "ploc_radius") s.ploc_radius = (int)std::min<int64_t>(16, std::max<int64_t>(1, value)), s.bvh_valid = false;
+    else if (n == "collapse") s.collapse = value != 0, s.bvh_valid = false, s.blas_valid = false;
+    else if (n == "collapse_prim_cost_pct") s.collapse_prim_cost_pct = (int)std::min<int64_t>(1000, std::max<int64_t>(1, value)), s.bvh_valid = false, s.blas_valid = false;
     else if (n == "l2_persist_mb") s.l2_persist_mb = (int)std::min<int64_t>(1024, std::max<int64_t>(0, value)), s.l2_dirty = true;
     else if (n == "l2_window_mb") s.l2_window_mb = (int)std::min<int64_t>(1 << 20, std::max<int64_t>(0, value)), s.l2_dirty = true;
     else return fail(PB2_ERR_ARG, "pb2_scene_set_option: unknown option " + n);

@@ -87,5 +87,7 @@ struct SceneView {
     uint32_t n_nodes;
     uint32_t n_prims;
     uint32_t root; // node the traversal starts at: the top-level tree's root (it sits behind the bottom-level trees in `nodes`)
+    uint32_t plane_bias; // 0x47000000 (2^15): operand of the PRMT that turns plane bytes into floats (node_step).  A kernel parameter
+                         // on purpose: PRMT takes ONE immediate, and a literal here makes the compiler route the selectors through registers
 };
 }// namespace pb2

@@ -53,6 +53,10 @@ struct Scene {
     bool blas_valid = false;     // the bottom-level trees match the meshes and instances: only the top level needs rebuilding
     int builder = 0; // 0 LBVH, 1 binned SAH sweep along the Morton order, 2 SAH-driven bottom-up clustering (bvh_ploc.cu)
     int ploc_radius = 8; // neighbours searched on either side along the Morton curve (builder 2)
+    // binary tree -> BVH8: 1 = the cut that minimises the SAH cost of the wide tree (tables filled bottom-up by k_refit<true>; LBVH
+    // and the top level), 0 = greedy expansion of the child with the largest surface area.  collapse_prim_cost_pct: cost of one
+    // primitive test in per cent of one wide-node test
+    int collapse = 1, collapse_prim_cost_pct = 30;
     pb2_build_stats build_stats{};
 
     // options

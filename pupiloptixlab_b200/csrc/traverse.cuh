@@ -19,6 +19,10 @@ namespace pb2 {
 #ifndef PB2_APPROX_IDIR
 #define PB2_APPROX_IDIR 1
 #endif
+// quantised plane bytes -> float through PRMT + the FMA that follows instead of I2F.U8 (node_step)
+#ifndef PB2_NODE_PRMT
+#define PB2_NODE_PRMT 1
+#endif
 #ifndef PB2_STACK_SIZE
 #define PB2_STACK_SIZE 32
 #endif
@@ -142,6 +146,9 @@ struct RayState {
 };
 
 // reciprocal direction and octant of r.d (again after an instance transform)
+// direction components below this magnitude are treated as this magnitude by the slab tests: 1 / d stays far enough from the
+// top of the fp32 range for the products of node_step (32768 * scale / d) in any scene smaller than 1e15 units
+constexpr float kMinDir = 1e-18f;
 PB2_D void ray_set_dir(RayState &r, float3 d) {
 #if PB2_APPROX_IDIR
     // 1 / d feeds the slab tests only (never t, u, v), which are conservative by construction: the one-instruction hardware
@@ -149,11 +156,11 @@ PB2_D void ray_set_dir(RayState &r, float3 d) {
     // reciprocals 9 % of k_extend's instructions and 10 % of its stall samples on the Cornell box.
     auto safe_inv = [](float x) {
         float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(x) > kMinDir ? x : copysignf(kMinDir, x)));
         return r;
     };
 #else
-    auto safe_inv = [](float x) { return __frcp_rn(fabsf(x) > 1e-30f ? x : copysignf(1e-30f, x)); }; // IEEE whatever the compile flags say
+    auto safe_inv = [](float x) { return __frcp_rn(fabsf(x) > kMinDir ? x : copysignf(kMinDir, x)); }; // IEEE whatever the compile flags say
 #endif
     r.d = d;
     r.idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
@@ -250,6 +257,19 @@ PB2_D bool node_step(const SceneView &sv, RayState &r, const TravStack &stack, c
     const float3 org = mk3((n0.x - r.o.x) * r.idir.x, (n0.y - r.o.y) * r.idir.y, (n0.z - r.o.z) * r.idir.z);
     constexpr float kFar = PB2_APPROX_IDIR ? 1.0000007f : 1.0000004f; // far planes pushed out by a few ulps: rounding can never cull a touched box
     const float3 adj_f = adj * kFar, org_f = org * kFar;
+#if PB2_NODE_PRMT
+    // Plane byte b -> float without the conversion unit: PRMT drops b into mantissa bits 8..15 of 2^15, which reads 32768 + b,
+    // and the bias moves into the addend of the multiply-add that follows: (32768 + b) adj + (org - 32768 adj).  The addend is
+    // rounded DOWN for near planes and UP for far planes, so the box only ever grows (by at most 2^-8 of a quantisation step).
+    // I2F.U8 runs on the quarter-rate XU pipe (ncu: the busiest pipe of the trace kernels, 48 conversions per wide node).
+    const float3 org_n = mk3(__fmaf_rd(-32768.f, adj.x, org.x), __fmaf_rd(-32768.f, adj.y, org.y), __fmaf_rd(-32768.f, adj.z, org.z));
+    const float3 org_ff = mk3(__fmaf_ru(-32768.f, adj_f.x, org_f.x), __fmaf_ru(-32768.f, adj_f.y, org_f.y), __fmaf_ru(-32768.f, adj_f.z, org_f.z));
+    const uint32_t bias = sv.plane_bias; // 2^15, from the constant bank (SceneView)
+#define PB2_PLANE(w, j) __uint_as_float(__byte_perm((w), bias, 0x7504u | ((j) << 4)))
+#else
+    const float3 org_n = org, org_ff = org_f;
+#define PB2_PLANE(w, j) ((float)byte_of((w), (j)))
+#endif
     uint32_t hitmask = 0;
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
@@ -265,14 +285,15 @@ PB2_D bool node_step(const SceneView &sv, RayState &r, const TravStack &stack, c
         const uint32_t nz = pz ? qlz : qhz, fz = pz ? qhz : qlz;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float tnx = (float)byte_of(nx, j) * adj.x + org.x, tfx = (float)byte_of(fx, j) * adj_f.x + org_f.x;
-            const float tny = (float)byte_of(ny, j) * adj.y + org.y, tfy = (float)byte_of(fy, j) * adj_f.y + org_f.y;
-            const float tnz = (float)byte_of(nz, j) * adj.z + org.z, tfz = (float)byte_of(fz, j) * adj_f.z + org_f.z;
+            const float tnx = PB2_PLANE(nx, j) * adj.x + org_n.x, tfx = PB2_PLANE(fx, j) * adj_f.x + org_ff.x;
+            const float tny = PB2_PLANE(ny, j) * adj.y + org_n.y, tfy = PB2_PLANE(fy, j) * adj_f.y + org_ff.y;
+            const float tnz = PB2_PLANE(nz, j) * adj.z + org_n.z, tfz = PB2_PLANE(fz, j) * adj_f.z + org_ff.z;
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, r.tmin));
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, r.hit.t));
             if (tn <= tf) hitmask |= byte_of(child_bits4, j) << byte_of(bit_index4, j);
         }
     }
+#undef PB2_PLANE
     r.G = make_uint2(n1.x, (hitmask & 0xff000000u) | (ebits >> 24));
     r.T = hitmask & 0x00ffffffu;
     r.prim_base = n1.y;

@@ -130,6 +130,8 @@ def _declare(lib):
     lib.orc_num_triangles.argtypes = [C.c_void_p]
     lib.orc_num_triangles.restype = C.c_uint64
     lib.orc_trace_closest.argtypes = [C.c_void_p, P(f32), C.c_uint64, C.c_void_p, C.c_int, C.c_int, P(C.c_uint64)]
+    if hasattr(lib, "orc_trace_closest_objspace"):
+        lib.orc_trace_closest_objspace.argtypes = [C.c_void_p, P(f32), C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]
     lib.orc_trace_any.argtypes = [C.c_void_p, P(f32), C.c_uint64, P(C.c_uint8), C.c_int]
     lib.orc_hit_geometry.argtypes = [C.c_void_p, C.c_void_p, P(f32), P(f32), P(f32), P(f32), P(C.c_int)]
     lib.orc_camera_rays.argtypes = [C.c_void_p, u32, P(f32)]
@@ -337,6 +339,14 @@ class OracleScene:
         tests = C.c_uint64()
         self.lib.orc_trace_closest(self.h, fp(rays), rays.shape[0], hits.ctypes.data, int(brute), threads, C.byref(tests))
         return hits, tests.value
+
+    def trace_closest_objspace(self, rays, objspace, threads=0):
+        """exhaustive loop; instances with objspace[i] != 0 are intersected in object space (a mesh behind an instance node)"""
+        rays = np.ascontiguousarray(rays, np.float32)
+        flags = np.ascontiguousarray(objspace, np.uint8)
+        hits = np.zeros(rays.shape[0], HIT_DTYPE)
+        self.lib.orc_trace_closest_objspace(self.h, fp(rays), rays.shape[0], hits.ctypes.data, flags.ctypes.data, threads)
+        return hits
 
     def trace_any(self, rays, brute=False):
         rays = np.ascontiguousarray(rays, np.float32)

@@ -104,6 +104,15 @@ def test_instanced_scene_matches_the_flattened_oracle(port_lib, coop):
     _check_t(rays, gpu, ref, meshes, [osc.instance_xform(i)[:3] for i in range(len(desc.shapes))])
     inst_hits = np.count_nonzero((ref["inst"] >= 0) & (ref["inst"] < 7))
     assert inst_hits > 1500, inst_hits  # the instanced placements are actually hit
+    # the same loop with the seven placements intersected in OBJECT space, as the instance nodes do (the ray through the
+    # fp32 inverse of the placement, the mesh's own triangles): every hit bit for bit, ids without any tie allowance
+    flags = np.zeros(len(desc.shapes), np.uint8)
+    flags[:7] = 1
+    obj = osc.trace_closest_objspace(rays, flags)
+    assert np.array_equal(gpu["inst"], obj["inst"]) and np.array_equal(gpu["prim"], obj["prim"])
+    hit = obj["inst"] >= 0
+    for f in ("t", "u", "v"):
+        assert np.array_equal(gpu[f][hit].view(np.uint32), obj[f][hit].view(np.uint32)), f
     m = (gpu["inst"] == ref["inst"]) & (gpu["prim"] == ref["prim"]) & (ref["inst"] >= 0)
     assert np.allclose(gpu["u"][m], ref["u"][m], atol=5e-4) and np.allclose(gpu["v"][m], ref["v"][m], atol=5e-4)
     rays[:, 7] = np.random.default_rng(1).uniform(0.5, 25.0, len(rays)).astype(np.float32)

@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--l2", type=str, default="", help="comma list of persist_mb:window_mb pairs for the L2 access-policy window over the top of the node array")
     ap.add_argument("--coop", type=int, default=-1, help="warp-cooperative primitive tests: 1 on, 0 off, -1 auto")
     ap.add_argument("--ploc-radius", type=int, default=0, help="builder 2: neighbours searched on either side along the Morton curve")
+    ap.add_argument("--collapse", type=int, default=-1, help="binary tree -> BVH8: 1 SAH-optimal cut (default), 0 greedy largest-area expansion")
+    ap.add_argument("--prim-cost", type=int, default=0, help="collapse = 1: cost of a primitive test in per cent of a wide-node test")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check of 8192 sampled rays per batch against the oracle's CPU BVH")
     args = ap.parse_args()
     import torch
@@ -60,6 +62,10 @@ def main():
     builds = [bs.build_ms]
     if args.ploc_radius:
         pupil.scene_handle().set_option("ploc_radius", args.ploc_radius)
+    if args.collapse >= 0:
+        pupil.scene_handle().set_option("collapse", args.collapse)
+    if args.prim_cost:
+        pupil.scene_handle().set_option("collapse_prim_cost_pct", args.prim_cost)
     for _ in range(2):  # rebuild twice more: steady-state build time (allocator warm)
         pupil.set_bvh_builder(args.builder if args.builder >= 0 else 0)
         builds.append(pupil.build_stats().build_ms)
