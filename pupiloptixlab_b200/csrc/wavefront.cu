@@ -523,11 +523,21 @@ __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_s
     // MULTI: all eight material queues in one launch (SORTED with ONLY < 0, kept for A/B runs); otherwise one queue — the
     // extension queue itself (unsorted), or material queue ONLY of the sorted mode, one launch per material type of the scene
     constexpr bool MULTI = SORTED && ONLY < 0;
-    uint32_t start[kNumTypes + 1];
-    start[0] = 0;
+    // first virtual index and length of every material queue, once per CTA in shared memory (as a per-thread array it was spilled:
+    // ncu charged the look-up below 18 M local-memory sectors per launch)
+    __shared__ uint32_t start[kNumTypes + 1], s_count[kNumTypes];
     if (MULTI) {
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
 #pragma unroll
-        for (int t = 0; t < kNumTypes; ++t) start[t + 1] = start[t] + ((counts[t] + kShadeMask) & ~kShadeMask);
+            for (int t = 0; t < kNumTypes; ++t) {
+                const uint32_t c = counts[t];
+                start[t] = run, s_count[t] = c;
+                run += (c + kShadeMask) & ~kShadeMask;
+            }
+            start[kNumTypes] = run;
+        }
+        __syncthreads();
     }
     if (SORTED && !MULTI) queue += (size_t)ONLY * capacity;
     const uint32_t n_single = MULTI ? 0u : counts[SORTED ? ONLY : 0]; // read once: the loop below would reload it from memory every iteration
@@ -540,7 +550,7 @@ __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_s
 #pragma unroll
             for (int k = 1; k < kNumTypes; ++k) t += vi >= start[k] ? 1 : 0;
             const uint32_t local = vi - start[t];
-            if (local >= counts[t]) return false;
+            if (local >= s_count[t]) return false;
             p = queue[(size_t)t * capacity + local];
         } else {
             if (vi >= n_single) return false;
@@ -551,12 +561,30 @@ __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_s
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t p_next = 0, iter = 0;
     bool valid_next = blockIdx.x * blockDim.x + threadIdx.x < total && fetch(blockIdx.x * blockDim.x + threadIdx.x, p_next);
+#if PB2_SHADE_PREFETCH >= 5
+    // Two entries ahead: the queue entry of iteration i + 2 is LOADED while path i is shaded, and the records of path i + 1 —
+    // whose queue entry was loaded an iteration ago and is in its register by now — are requested before path i is shaded.
+    // (The one-deep variants 1 .. 4 asked for the records right after loading their queue entry and waited for it on the spot.)
+    uint32_t p_after = 0;
+    bool valid_after = blockIdx.x * blockDim.x + threadIdx.x + stride < total && fetch(blockIdx.x * blockDim.x + threadIdx.x + stride, p_after);
+#endif
     for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total; vi += stride) { // total % 128 == 0: CTA-uniform
         uint32_t emitted = 0;
         const uint32_t p = p_next;
         const bool valid = valid_next;
         ShadowRay sh;
-#if PB2_SHADE_PREFETCH
+#if PB2_SHADE_PREFETCH >= 5
+        p_next = p_after, valid_next = valid_after;
+        if (valid_next) {
+#if PB2_SHADE_PREFETCH == 5
+            prefetch_l2(pa.hit + p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.thr + p_next);
+#else
+            prefetch_l1(pa.hit + p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.thr + p_next);
+#endif
+        }
+        valid_after = vi + 2 * stride < total && fetch(vi + 2 * stride, p_after);
+#endif
+#if PB2_SHADE_PREFETCH && PB2_SHADE_PREFETCH < 5
         // the next iteration's queue entry is fetched now and its three 32-byte records are requested while this path is
         // shaded: ncu showed a third of k_shade's stall samples waiting on exactly these loads (profiles/r1c_ncu.md)
         valid_next = vi + stride < total && fetch(vi + stride, p_next);
@@ -571,7 +599,7 @@ __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_s
 #endif
 #endif
         if (valid) emitted = shade_path<ONLY>(sv, pa, fp, out, p, sh);
-#if PB2_SHADE_PREFETCH >= 3
+#if PB2_SHADE_PREFETCH == 3 || PB2_SHADE_PREFETCH == 4
         // variant: the queue entry has arrived by now, so the prefetches do not wait for it
         if (valid_next) {
 #if PB2_SHADE_PREFETCH == 3
