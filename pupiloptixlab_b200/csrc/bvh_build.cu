@@ -296,6 +296,16 @@ __global__ void k_refit(BinTree t, const uint32_t *__restrict__ sorted, const fl
     }
 }
 
+// parent links of a binary tree that came without them (the clustering and the sweep builders): what k_refit<true> climbs
+__global__ void __launch_bounds__(256) k_parents(BinTree t, int root) {
+    const int n = t.n, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int lc = t.left[i], rc = t.right[i];
+    t.parent[lc >= 0 ? lc : (n - 1) + ~lc] = i;
+    t.parent[rc >= 0 ? rc : (n - 1) + ~rc] = i;
+    if (i == root) t.parent[i] = -1;
+}
+
 // ---- stage 5: collapse -----------------------------------------------------------------------------------
 struct CollapseCtx {
     BinTree t;
@@ -642,6 +652,18 @@ void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, 
                 k_refit<false><<<div_up(n, 256), 256, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr, inst_leaves ? prims_in.ptr : nullptr, CostTab{});
             }
             PB2_LAUNCH_CHECK();
+        }
+        if (n > 1 && s.collapse == 1 && !cost_word.ptr) {
+            // the builders that bring their own boxes: one more bottom-up sweep for the cost tables (it recomputes the same boxes)
+            k_parents<<<div_up(n - 1, 256), 256, 0, st>>>(t, root_ref);
+            PB2_LAUNCH_CHECK();
+            DevBuf<int> arrive(n);
+            arrive.zero(st);
+            cost_c.alloc(2 * (size_t)n), cost_word.alloc(n);
+            const CostTab ct{ cost_c.ptr, cost_word.ptr, (float)s.collapse_prim_cost_pct * 0.01f };
+            k_refit<true><<<div_up(n, 256), 256, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr, nullptr, ct);
+            PB2_LAUNCH_CHECK();
+            PB2_CUDA(cudaStreamSynchronize(st));
         }
         PB2_CUDA(cudaStreamSynchronize(st)); // tmp / arrive / keys go out of scope
     }
