@@ -561,30 +561,12 @@ __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_s
     const uint32_t stride = gridDim.x * blockDim.x;
     uint32_t p_next = 0, iter = 0;
     bool valid_next = blockIdx.x * blockDim.x + threadIdx.x < total && fetch(blockIdx.x * blockDim.x + threadIdx.x, p_next);
-#if PB2_SHADE_PREFETCH >= 5
-    // Two entries ahead: the queue entry of iteration i + 2 is LOADED while path i is shaded, and the records of path i + 1 —
-    // whose queue entry was loaded an iteration ago and is in its register by now — are requested before path i is shaded.
-    // (The one-deep variants 1 .. 4 asked for the records right after loading their queue entry and waited for it on the spot.)
-    uint32_t p_after = 0;
-    bool valid_after = blockIdx.x * blockDim.x + threadIdx.x + stride < total && fetch(blockIdx.x * blockDim.x + threadIdx.x + stride, p_after);
-#endif
     for (uint32_t vi = blockIdx.x * blockDim.x + threadIdx.x; vi < total; vi += stride) { // total % 128 == 0: CTA-uniform
         uint32_t emitted = 0;
         const uint32_t p = p_next;
         const bool valid = valid_next;
         ShadowRay sh;
-#if PB2_SHADE_PREFETCH >= 5
-        p_next = p_after, valid_next = valid_after;
-        if (valid_next) {
-#if PB2_SHADE_PREFETCH == 5
-            prefetch_l2(pa.hit + p_next), prefetch_l2(pa.ray + 2 * (size_t)p_next), prefetch_l2(pa.thr + p_next);
-#else
-            prefetch_l1(pa.hit + p_next), prefetch_l1(pa.ray + 2 * (size_t)p_next), prefetch_l1(pa.thr + p_next);
-#endif
-        }
-        valid_after = vi + 2 * stride < total && fetch(vi + 2 * stride, p_after);
-#endif
-#if PB2_SHADE_PREFETCH && PB2_SHADE_PREFETCH < 5
+#if PB2_SHADE_PREFETCH
         // the next iteration's queue entry is fetched now and its three 32-byte records are requested while this path is
         // shaded: ncu showed a third of k_shade's stall samples waiting on exactly these loads (profiles/r1c_ncu.md)
         valid_next = vi + stride < total && fetch(vi + stride, p_next);
@@ -599,7 +581,7 @@ __global__ void __launch_bounds__(kShadeThreads, MINB * 128 / kShadeThreads) k_s
 #endif
 #endif
         if (valid) emitted = shade_path<ONLY>(sv, pa, fp, out, p, sh);
-#if PB2_SHADE_PREFETCH == 3 || PB2_SHADE_PREFETCH == 4
+#if PB2_SHADE_PREFETCH >= 3
         // variant: the queue entry has arrived by now, so the prefetches do not wait for it
         if (valid_next) {
 #if PB2_SHADE_PREFETCH == 3
