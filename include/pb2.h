@@ -227,7 +227,8 @@ int pb2_render_stats_get(pb2_scene *scene, pb2_render_stats *stats); /* synchron
  * by scene size), l2_persist_mb / l2_window_mb (persisting-L2 access-policy window over the top levels of the node array;
  * 0 = off, the default), ploc_radius (builder 2: neighbours searched on either side, 1..16, default 8), instancing (0 | 1 | 2, see pb2_bvh_build),
  * collapse (binary tree -> BVH8: 1 = SAH-optimal cut by dynamic programming, the default; 0 = greedy largest-area expansion) and
- * collapse_prim_cost_pct (cost of a primitive test in per cent of a wide-node test, default 30).  Unknown names fail with PB2_ERR_ARG. */
+ * collapse_prim_cost_pct (cost of a primitive test in per cent of a wide-node test, default 30), morton_bits (leading bits of the
+ * 63-bit Morton key that are sorted, 15..63; 0 = chosen by primitive count, the default).  Unknown names fail with PB2_ERR_ARG. */
 int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value);
 /* frame[i] = (sum[i].xyz / total_spp, 1) on the scene's stream: the last step of a sharded render whose sums were combined
  * by the caller's own collective (pb2_comm_reduce_frames below does both).   */

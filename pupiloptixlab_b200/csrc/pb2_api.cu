@@ -618,6 +618,7 @@ int pb2_scene_set_option(pb2_scene *scene, const char *name, int64_t value) {
     else if (n == "paths_in_flight") s.paths_in_flight = (uint64_t)std::max<int64_t>(0, value);
     else if (n == "instancing") s.instancing = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)), s.bvh_valid = false, s.blas_valid = false;
     else if (n == "ploc_radius") s.ploc_radius = (int)std::min<int64_t>(16, std::max<int64_t>(1, value)), s.bvh_valid = false;
+    else if (n == "morton_bits") s.morton_bits = value <= 0 ? 0 : (int)std::min<int64_t>(63, std::max<int64_t>(15, value)), s.bvh_valid = false, s.blas_valid = false;
     else if (n == "collapse") s.collapse = value != 0, s.bvh_valid = false, s.blas_valid = false;
     else if (n == "collapse_prim_cost_pct") s.collapse_prim_cost_pct = (int)std::min<int64_t>(1000, std::max<int64_t>(1, value)), s.bvh_valid = false, s.blas_valid = false;
     else if (n == "l2_persist_mb") s.l2_persist_mb = (int)std::min<int64_t>(1024, std::max<int64_t>(0, value)), s.l2_dirty = true;

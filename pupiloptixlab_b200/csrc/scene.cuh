@@ -57,6 +57,7 @@ struct Scene {
     // and the top level), 0 = greedy expansion of the child with the largest surface area.  collapse_prim_cost_pct: cost of one
     // primitive test in per cent of one wide-node test
     int collapse = 1, collapse_prim_cost_pct = 30;
+    int morton_bits = 0; // leading bits of the 63-bit Morton key that are sorted (and seen by the radix tree), 8 per sort pass; 0 = by primitive count
     pb2_build_stats build_stats{};
 
     // options

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--ploc-radius", type=int, default=0, help="builder 2: neighbours searched on either side along the Morton curve")
     ap.add_argument("--collapse", type=int, default=-1, help="binary tree -> BVH8: 1 SAH-optimal cut (default), 0 greedy largest-area expansion")
     ap.add_argument("--prim-cost", type=int, default=0, help="collapse = 1: cost of a primitive test in per cent of a wide-node test")
+    ap.add_argument("--morton-bits", type=int, default=0, help="leading bits of the 63-bit Morton key that are sorted (8 per sort pass)")
     ap.add_argument("--no-check", action="store_true", help="skip the parity check of 8192 sampled rays per batch against the oracle's CPU BVH")
     args = ap.parse_args()
     import torch
@@ -64,6 +65,8 @@ def main():
         pupil.scene_handle().set_option("ploc_radius", args.ploc_radius)
     if args.collapse >= 0:
         pupil.scene_handle().set_option("collapse", args.collapse)
+    if args.morton_bits:
+        pupil.scene_handle().set_option("morton_bits", args.morton_bits)
     if args.prim_cost:
         pupil.scene_handle().set_option("collapse_prim_cost_pct", args.prim_cost)
     for _ in range(2):  # rebuild twice more: steady-state build time (allocator warm)
