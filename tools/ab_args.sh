@@ -4,6 +4,6 @@ mkdir -p gpurun_out
 i=0
 for a in "$@"; do
   i=$((i+1)); echo "== $a"
-  timeout 200 python tools/bench_traversal.py --no-check $a > gpurun_out/ab_args_$i.jsonl 2> gpurun_out/ab_args_$i.err; echo "  rc=$?"
+  timeout -k 10 200 python tools/bench_traversal.py --no-check $a > gpurun_out/ab_args_$i.jsonl 2> gpurun_out/ab_args_$i.err; echo "  rc=$?"
   python tools/fmt_traversal.py < gpurun_out/ab_args_$i.jsonl; tail -2 gpurun_out/ab_args_$i.err
 done

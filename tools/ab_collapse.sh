@@ -7,6 +7,6 @@ shift
 for v in $variants; do
   c=${v%%:*}; p=${v##*:}
   echo "== collapse $c prim cost $p"
-  timeout 200 python tools/bench_traversal.py --collapse $c --prim-cost $p --no-check "$@" > gpurun_out/ab_collapse_${c}_${p}.jsonl 2> gpurun_out/ab_collapse_${c}_${p}.err; echo "  rc=$?"
+  timeout -k 10 200 python tools/bench_traversal.py --collapse $c --prim-cost $p --no-check "$@" > gpurun_out/ab_collapse_${c}_${p}.jsonl 2> gpurun_out/ab_collapse_${c}_${p}.err; echo "  rc=$?"
   python tools/fmt_traversal.py < gpurun_out/ab_collapse_${c}_${p}.jsonl; tail -3 gpurun_out/ab_collapse_${c}_${p}.err
 done

@@ -3,9 +3,9 @@
 mkdir -p gpurun_out
 N=${1:-1}
 if [ "$N" = "1" ]; then
-timeout 400 python bench.py > gpurun_out/final_n1.json 2> gpurun_out/final_n1.err; echo rc=$?
+timeout -k 10 400 python bench.py > gpurun_out/final_n1.json 2> gpurun_out/final_n1.err; echo rc=$?
 else
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/final_n$N.json 2> gpurun_out/final_n$N.err; echo rc=$?
+timeout -k 10 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/final_n$N.json 2> gpurun_out/final_n$N.err; echo rc=$?
 fi
 python - <<PY
 import json
