@@ -10,8 +10,8 @@
 //   1 emit_prims      instance triangles / spheres -> 48 B world-space records + AABBs + scene bounds
 //   2 morton + sort   63-bit keys, in-tree onesweep radix sort (radix_sort.cu)
 //   3 radix_tree      Karras 2012 binary radix tree (ties broken by index)
-//   4 refit           bottom-up AABBs with per-node arrival counters
-//   5 collapse        breadth-first: binary subtree -> up to 8 children by largest-area expansion,
+//   4 refit           bottom-up AABBs and, for the cost-optimal collapse, the SAH cost tables + decisions of every binary node
+//   5 collapse        breadth-first: binary subtree -> up to 8 children along the cheapest cut (or by largest-area expansion),
 //                     octant slot assignment, quantisation, leaf primitive copy
 #include "scene.cuh"
 #include "traverse.cuh"
@@ -624,6 +624,18 @@ struct LevelOut {
     float sah = 0.f, lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
 };
 
+// 36 bytes per binary node for the cost-optimal collapse; a scene too large for them falls back to the greedy cut instead of failing
+bool alloc_cost_tables(DevBuf<float4> &cost_c, DevBuf<uint32_t> &cost_word, uint32_t n) {
+    try {
+        cost_c.alloc(2 * (size_t)n), cost_word.alloc(n);
+        return true;
+    } catch (const CudaError &) {
+        cudaGetLastError();
+        cost_c.release(), cost_word.release();
+        return false;
+    }
+}
+
 // Stages 2-5 over n emitted records (prims_in, box_lo / box_hi, bounds): Morton sort, binary tree, collapse, scatter of the
 // records into prims_out (their final place).  inst_leaves: records of kind 2 become instance nodes (top level of a two-level scene).
 void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, DevBuf<PrimRec> &prims_in, DevBuf<float4> &box_lo, DevBuf<float4> &box_hi,
@@ -670,8 +682,7 @@ void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, 
             PB2_LAUNCH_CHECK();
             DevBuf<int> arrive(n);
             arrive.zero(st);
-            if (s.collapse == 1) {
-                cost_c.alloc(2 * (size_t)n), cost_word.alloc(n);
+            if (s.collapse == 1 && alloc_cost_tables(cost_c, cost_word, n)) {
                 const CostTab ct{ cost_c.ptr, cost_word.ptr, (float)s.collapse_prim_cost_pct * 0.01f };
                 k_refit<true><<<div_up(n - 1, kRefitBlock), kRefitBlock, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr, inst_leaves ? prims_in.ptr : nullptr, ct);
             } else {
@@ -679,13 +690,12 @@ void build_level(Scene &s, cudaStream_t st, uint32_t n, uint32_t n_inst_leaves, 
             }
             PB2_LAUNCH_CHECK();
         }
-        if (n > 1 && s.collapse == 1 && !cost_word.ptr) {
+        if (n > 1 && s.collapse == 1 && !cost_word.ptr && s.builder != 0 && !inst_leaves && alloc_cost_tables(cost_c, cost_word, n)) {
             // the builders that bring their own boxes: one more bottom-up sweep for the cost tables (it recomputes the same boxes)
             k_parents<<<div_up(n - 1, 256), 256, 0, st>>>(t, root_ref);
             PB2_LAUNCH_CHECK();
             DevBuf<int> arrive(n);
             arrive.zero(st);
-            cost_c.alloc(2 * (size_t)n), cost_word.alloc(n);
             const CostTab ct{ cost_c.ptr, cost_word.ptr, (float)s.collapse_prim_cost_pct * 0.01f };
             k_refit<true><<<div_up(n - 1, kRefitBlock), kRefitBlock, 0, st>>>(t, sorted.ptr, box_lo.ptr, box_hi.ptr, arrive.ptr, nullptr, ct);
             PB2_LAUNCH_CHECK();
