@@ -255,16 +255,26 @@ constexpr int kRefitBlock = PB2_REFIT_BLOCK;
 // the internal nodes with two leaf children, packed (warp-aggregated append; their order does not matter): k_refit starts one
 // thread at each, so its warps begin with 32 working lanes instead of the ~8 a launch over all internal nodes leaves
 // (ncu, 30 M triangles: 3.6 of 32 lanes active on average, 2.5 G warp instructions)
-__global__ void __launch_bounds__(256) k_refit_seeds(BinTree t, int *__restrict__ seeds, uint32_t *__restrict__ n_seeds) {
+__global__ void __launch_bounds__(1024) k_refit_seeds(BinTree t, int *__restrict__ seeds, uint32_t *__restrict__ n_seeds) {
+    __shared__ uint32_t s_warp[32], s_base; // one atomic per CTA: a million warps adding to one word serialise (0.65 ms for 30 M nodes)
     const int n = t.n, i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool seed = i < n - 1 && t.left[i] < 0 && t.right[i] < 0;
-    const uint32_t m = __ballot_sync(0xffffffffu, seed);
-    if (!m) return;
-    const uint32_t lane = threadIdx.x & 31u;
-    uint32_t base = 0;
-    if (lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(n_seeds, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-    if (seed) seeds[base + __popc(m & ((1u << lane) - 1u))] = i;
+    const uint32_t m = __ballot_sync(0xffffffffu, seed), lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t c = s_warp[lane];
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if ((int)lane >= d) incl += up;
+        }
+        s_warp[lane] = incl - c;
+        if (lane == 31) s_base = incl ? atomicAdd(n_seeds, incl) : 0u;
+    }
+    __syncthreads();
+    if (seed) seeds[s_base + s_warp[warp] + __popc(m & ((1u << lane) - 1u))] = i;
 }
 template<bool COST>
 __global__ void __launch_bounds__(kRefitBlock) k_refit(BinTree t, const uint32_t *__restrict__ sorted, const float4 *__restrict__ box_lo, const float4 *__restrict__ box_hi,
@@ -640,7 +650,7 @@ struct LevelOut {
 void refit_seeds(cudaStream_t st, const BinTree &t, DevBuf<int> &seeds, DevBuf<uint32_t> &n_seeds) {
     seeds.ensure(t.n / 2 + 1), n_seeds.ensure(1);
     n_seeds.zero(st);
-    k_refit_seeds<<<div_up(t.n - 1, 256), 256, 0, st>>>(t, seeds.ptr, n_seeds.ptr);
+    k_refit_seeds<<<div_up(t.n - 1, 1024), 1024, 0, st>>>(t, seeds.ptr, n_seeds.ptr);
     PB2_LAUNCH_CHECK();
 }
 // 36 bytes per binary node for the cost-optimal collapse; a scene too large for them falls back to the greedy cut instead of failing
