@@ -363,6 +363,12 @@ def c4_record(torch, pupil, stream, args, peak):
     inco, p = rb.bounce_rays(pos, 1 << 21, rng)
     out["incoherent"] = rb.measure_trace(torch, scene, stream, inco, False, 5, peak, "closest_incoherent_bounce")[0]
     out["any_hit"] = rb.measure_trace(torch, scene, stream, rb.shadow_rays(p, rng), True, 5, peak, "anyhit_shadow_to_light")[0]
+    # the same two distributions in renderer-sized launches (16 Mi rays, origins resampled with replacement): a 2^21-ray batch gives
+    # each resident lane ~14 rays, so the drain of the persistent kernel is a visible share of a 1.3 ms launch
+    big, pb = rb.bounce_rays(pos, 1 << 24, rng)
+    out["incoherent_16mi"] = rb.measure_trace(torch, scene, stream, big, False, 3, peak, "closest_incoherent_bounce, 16 Mi rays in one launch")[0]
+    del big
+    out["any_hit_16mi"] = rb.measure_trace(torch, scene, stream, rb.shadow_rays(pb, rng), True, 3, peak, "anyhit_shadow_to_light, 16 Mi rays in one launch")[0]
     return out
 
 
